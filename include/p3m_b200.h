@@ -1,0 +1,193 @@
+/* include/p3m_b200.h -- the drop-in boundary of the B200-native P3M / PM force step.
+ *
+ * A plain C ABI (extern "C", pointers + sizes, no C++/torch types) implemented by
+ * particlesimulation_b200/libp3m_b200.so (hand-written sm_100a CUDA kernels + cuFFT).  The reference
+ * (AleksyBalazinski/ParticleSimulation) has no FFI layer -- its boundary is the C++ class API -- so
+ * each entry point below names the reference member function(s) whose body it replaces; the
+ * API-compatible C++ classes in particlesimulation_b200/host/ (PMMethod, P3MMethod, ...) are thin
+ * callers of this ABI.  Reference citations are file:line under the reference checkout.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative P3M_E* code otherwise; p3m_last_error() gives
+ *    the message of the last failure on the calling thread.  No exceptions cross the boundary.
+ *  - a context is bound to one GPU and must be driven by one host thread at a time (the reference's
+ *    run loops are not re-entrant either: file-scope timers, shared Grid).
+ *  - "host" pointers are ordinary host memory (pinned or pageable); particle arrays are packed xyz
+ *    triples (Vec3 layout, include/vec3.h:5-8) in ORIGINAL particle order, i.e. index i here is
+ *    particles[i] of PMMethod::getParticles() (include/pmMethod.h:33).
+ *  - meshes are x-fastest, flat = x + y*Nx + z*Nx*Ny (include/grid.h:52-54).
+ *  - all work is queued on the context's CUDA stream; readbacks synchronise that stream.
+ *  - there is NO CPU fallback: creating a context without a CUDA device fails with P3M_ENODEV.
+ */
+#ifndef P3M_B200_H
+#define P3M_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P3M_OK 0
+#define P3M_EINVAL (-1)   /* bad argument / unknown enum (reference: std::invalid_argument) */
+#define P3M_ENODEV (-2)   /* no usable CUDA device */
+#define P3M_ECUDA (-3)    /* CUDA / cuFFT / NCCL runtime error */
+#define P3M_ESTATE (-4)   /* call order violated (e.g. force before particles were set) */
+#define P3M_ERANGE (-5)   /* a particle left the region the mesh kernels can address */
+
+/* include/pmConfig.h:3-5, include/greensFunctions.h:7 -- same enumerator order as the reference */
+enum { P3M_NGP = 0, P3M_CIC = 1, P3M_TSC = 2 };
+enum { P3M_TWO_POINT = 0, P3M_FOUR_POINT = 1 };
+enum { P3M_DISCRETE_LAPLACIAN = 0, P3M_S1_OPTIMAL = 1, P3M_S2_OPTIMAL = 2, P3M_POOR_MAN = 3 };
+enum { P3M_S1 = 0, P3M_S2 = 1 };
+enum { P3M_EXT_NONE = 0, P3M_EXT_SPH_RAD_DECR = 1 }; /* source/externalFields.cpp:4-15 */
+enum { P3M_F32 = 0, P3M_F64 = 1 };
+enum { P3M_UNITS_ORIGINAL = 0, P3M_UNITS_CODE = 1 };
+
+/* Everything the constructors PMMethod(...) (include/pmMethod.h:14-26) and P3MMethod(...)
+ * (include/p3mMethod.h:13-27) take, as a POD.  Physical quantities are in ORIGINAL units exactly as
+ * the reference's callers pass them (source/demos.cpp:736-776, 897-951). */
+typedef struct p3m_params {
+  int32_t nx, ny, nz;        /* Grid(gridPoints) include/grid.h:12 */
+  float box[3];              /* effectiveBoxSize == compBoxSize */
+  float H, DT, G;            /* cell size, time step, gravitational constant */
+  int32_t assignment;        /* P3M_NGP | P3M_CIC | P3M_TSC */
+  int32_t fd_scheme;         /* P3M_TWO_POINT | P3M_FOUR_POINT */
+  int32_t greens_function;   /* P3M_DISCRETE_LAPLACIAN | ... */
+  float particle_diameter;   /* PMMethod particleDiameter / P3MMethod particleDiameter */
+  int32_t p3m;               /* 0: PM only (PMMethod), 1: P3M (P3MMethod wraps PMMethod) */
+  float cutoff_radius;       /* P3MMethod cutoffRadius (re) */
+  float softening;           /* P3MMethod softeningLength */
+  int32_t cloud_shape;       /* P3M_S1 | P3M_S2 */
+  int32_t use_sr_table;      /* P3MMethod useSRForceTable (default true, include/p3mMethod.h:25) */
+  int32_t ext_kind;          /* externalField as a POD: P3M_EXT_NONE | P3M_EXT_SPH_RAD_DECR */
+  float ext_center[3];
+  float ext_R, ext_M;        /* sphRadDecrField(pos, center, R, M, G) */
+  int32_t precision;         /* P3M_F32 (the reference's precision) | P3M_F64 */
+  int32_t unit_roundtrip;    /* 1: reproduce the per-step code->original->code rounding of the run
+                                loops (source/pmMethod.cpp:94,113); 0: stay in code units */
+  int32_t green_zero_degenerate; /* 1 (recommended): G := 0 where every k_i in {0, N_i/2}: GreenOptimal
+                                is 0/0 rounding noise there and the mode carries no force */
+  int32_t device;            /* CUDA device ordinal; -1 = current device */
+  int32_t timing;            /* 1: bracket every phase with CUDA events (p3m_get_phase_ms) */
+} p3m_params;
+
+typedef struct p3m_ctx p3m_ctx;
+
+const char* p3m_last_error(void);
+int p3m_version(void);
+
+/* defaults as the reference demos use them: TSC, TWO_POINT, S1_OPTIMAL, DT = 1, table on */
+void p3m_default_params(p3m_params* p);
+
+/* PMMethod::PMMethod / P3MMethod::P3MMethod + Grid::Grid + FFTAdapter construction
+ * (source/pmMethod.cpp:30-60, source/p3mMethod.cpp:19-48, source/grid.cpp:5-19,
+ * source/chainingMesh.cpp:6-18): allocates device meshes, cuFFT plans, the short-range table. */
+int p3m_create(const p3m_params* params, p3m_ctx** out);
+int p3m_destroy(p3m_ctx* ctx);
+
+/* Particle upload.  units = P3M_UNITS_ORIGINAL applies stateToCodeUnits + massToCodeUnits on the
+ * device (source/unitConversions.cpp:23-71, include/unitConversions.h:8-50), as the head of run()
+ * does (source/pmMethod.cpp:72-73).  vel may be NULL (zeros).  Replaces the constructor's copy of
+ * `state`/`masses` into vector<Particle> and PMMethodGPU::copyParticlesHostToDevice
+ * (source/PMMethodGPU.cu:241-247). */
+int p3m_set_particles(p3m_ctx* ctx, const float* pos, const float* vel, const float* mass,
+                      int64_t n, int units);
+/* Download in original particle order; any pointer may be NULL.  acc is always in code units when
+ * units == P3M_UNITS_CODE, else converted with accelerationToOriginalUnits.  Replaces
+ * getParticles() / copyParticlesDeviceToHost (source/PMMethodGPU.cu:244-247). */
+int p3m_get_particles(p3m_ctx* ctx, float* pos, float* vel, float* acc, int units);
+int p3m_get_particles_f64(p3m_ctx* ctx, double* pos, double* vel, double* acc, int units);
+int64_t p3m_num_particles(const p3m_ctx* ctx);
+
+/* PMMethod::initGreensFunction (source/pmMethod.cpp:164-185) + GreenOptimal /
+ * GreenDiscreteLaplacian / GreenPoorMan (source/greensFunctions.cpp:122-220), evaluated on the
+ * device; stored Hermitian-symmetrised with the inverse FFT's 1/M folded in. */
+int p3m_green_init(p3m_ctx* ctx);
+/* Optional: install a caller-computed table instead (M values, the real part the reference stores
+ * in Grid::greensFunction).  Used by the parity tests to isolate the FFT from the table. */
+int p3m_set_green_table(p3m_ctx* ctx, const float* green_full_mesh);
+int p3m_set_green_table_f64(p3m_ctx* ctx, const double* green_full_mesh);
+/* Symmetrised table expanded back to the full mesh, without the 1/M factor. */
+int p3m_get_green_table(p3m_ctx* ctx, double* green_full_mesh);
+
+/* ---- the phases of one force evaluation, individually callable (each is parity-tested) ------- */
+/* A0: mesh cell + chaining-mesh cell of every particle (source/pmMethod.cpp:250-252,
+ * source/chainingMesh.cpp:25-29) and the cell sort that replaces ChainingMesh::fill /
+ * fillWithYSorting (source/chainingMesh.cpp:20-58). */
+int p3m_bin_sort(p3m_ctx* ctx);
+/* A1: PMMethod::spreadMass (source/pmMethod.cpp:200-277) */
+int p3m_deposit(p3m_ctx* ctx);
+/* A2+A3: Grid::fftDensity, PMMethod::findFourierPotential, Grid::invFftPotential
+ * (source/grid.cpp:50-56, source/pmMethod.cpp:340-350) */
+int p3m_poisson(p3m_ctx* ctx);
+/* A5: PMMethod::findFieldInCells (source/pmMethod.cpp:373-382) into an explicit field mesh.  Only
+ * needed by callers that read Grid::getField; p3m_gather computes the differences on the fly. */
+int p3m_gradient(p3m_ctx* ctx);
+/* A5+A6: PMMethod::updateAccelerations (source/pmMethod.cpp:384-390): finite differences of the
+ * potential fused with interpolation to the particles, plus the external field. */
+int p3m_gather(p3m_ctx* ctx);
+/* A7-A9: P3MMethod::calculateShortRangeForces + correctAccelerations
+ * (source/p3mMethod.cpp:50-57,168-192,247-322).  No-op (P3M_OK) for a PM-only context. */
+int p3m_short_range(p3m_ctx* ctx);
+/* PMMethod::pmMethodStep (source/pmMethod.cpp:137-144) [+ the two P3M calls above]:
+ * bin_sort, deposit, poisson, gather, short_range. */
+int p3m_force(p3m_ctx* ctx);
+
+/* A10: leapfrog free functions (source/leapfrog.cpp:5-24), code units. */
+int p3m_kick(p3m_ctx* ctx, float dt_factor);   /* v += dt_factor * a  (0.5 = setHalfStepVelocities) */
+int p3m_drift(p3m_ctx* ctx);                    /* x += v (+ unit round trip, + escape check) */
+/* A11: `steps` iterations of the run-loop body without recording (source/pmMethod.cpp:87-121,
+ * source/p3mMethod.cpp:101-153): drift, [escape check], force, kick.  Stops early when a particle
+ * escaped the computational box (PMMethod::escapedComputationalBox, source/pmMethod.cpp:146-156);
+ * *steps_done (may be NULL) receives the number of completed steps. */
+int p3m_step(p3m_ctx* ctx, int steps, int* steps_done);
+/* PMMethod::escapedComputationalBox on the current positions. */
+int p3m_escaped(p3m_ctx* ctx, int* escaped);
+
+/* N1: SimInfo diagnostics on the device (source/simInfo.cpp:50-127, source/pmMethod.cpp:97-105):
+ * out[0]=PE out[1]=KE out[2..4]=momentum out[5..7]=angular momentum out[8..10]=total external force
+ * (original units; momentum uses the integer-step velocity v + a/2). */
+int p3m_diagnostics(p3m_ctx* ctx, double out[11]);
+
+/* ---- readbacks for tests / Grid back-fill (PMMethodGPU::copyGridDensityToHost etc.,
+ * source/PMMethodGPU.cu:117-134) ------------------------------------------------------------- */
+int p3m_get_density(p3m_ctx* ctx, float* mesh);      /* M values, code units */
+int p3m_get_potential(p3m_ctx* ctx, float* mesh);    /* M values */
+int p3m_get_field(p3m_ctx* ctx, float* mesh_xyz);    /* 3M values (after p3m_gradient) */
+int p3m_get_density_f64(p3m_ctx* ctx, double* mesh);
+int p3m_get_potential_f64(p3m_ctx* ctx, double* mesh);
+int p3m_set_density(p3m_ctx* ctx, const float* mesh); /* test hook: feed the Poisson solve */
+int p3m_set_potential(p3m_ctx* ctx, const float* mesh);
+/* per particle (original order): PM mesh cell x + y*Nx + z*Nx*Ny of the truncated position, the
+ * chaining-mesh cell (or -1 for PM-only), and `order` = particle ids in sorted order. */
+int p3m_get_cells(p3m_ctx* ctx, int32_t* mesh_cell, int32_t* chain_cell, int32_t* order);
+int p3m_get_chaining_dims(p3m_ctx* ctx, int32_t dims[3]);
+/* ChainingMesh::getNeighborsAndSelf (source/chainingMesh.cpp:60-84): host-side geometry helper */
+int p3m_chaining_neighbors(const int32_t dims[3], int32_t cell, int32_t out14[14]);
+/* mesh part of the acceleration and short-range acceleration (= total SR force / mass), code units */
+int p3m_get_acc_parts(p3m_ctx* ctx, double* acc_pm, double* acc_sr);
+int p3m_get_sr_table(p3m_ctx* ctx, double* table500);
+
+/* ---- measurement -------------------------------------------------------------------------- */
+#define P3M_NPHASE 10
+/* accumulated CUDA-event milliseconds per phase since the last reset (timing must be enabled):
+ * 0 binSort 1 spreadMass 2 forwardFFT 3 fourierPotential 4 inverseFFT 5 fieldInCells+
+ * updateAccelerations (fused gather) 6 shortRangeForcesCalc 7 integrate 8 fieldInCells (explicit
+ * gradient) 9 comm -- names follow the reference's measureTime accumulators
+ * (source/pmMethod.cpp:21-28, source/p3mMethod.cpp:14-17). */
+int p3m_get_phase_ms(p3m_ctx* ctx, float ms[P3M_NPHASE], int reset);
+const char* p3m_phase_name(int i);
+/* exact pair statistics of the last p3m_short_range: pairs examined and pairs within the cutoff */
+int p3m_get_pair_counts(p3m_ctx* ctx, uint64_t* checked, uint64_t* in_range);
+/* kernels launched by this context so far (bench.py's gpu_launches) */
+int64_t p3m_launch_count(const p3m_ctx* ctx);
+/* the context's stream as a cudaStream_t, for event timing by the caller */
+void* p3m_stream(p3m_ctx* ctx);
+int p3m_synchronize(p3m_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P3M_B200_H */

@@ -1,0 +1,273 @@
+"""ctypes binding of the C ABI in include/p3m_b200.h (libp3m_b200.so).
+
+This is plumbing for tests and bench.py; the product is the shared library.  There is no CPU
+fallback: if the library is missing or no CUDA device is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libp3m_b200.so")
+
+NGP, CIC, TSC = 0, 1, 2
+TWO_POINT, FOUR_POINT = 0, 1
+DISCRETE_LAPLACIAN, S1_OPTIMAL, S2_OPTIMAL, POOR_MAN = 0, 1, 2, 3
+S1, S2 = 0, 1
+EXT_NONE, EXT_SPH_RAD_DECR = 0, 1
+F32, F64 = 0, 1
+UNITS_ORIGINAL, UNITS_CODE = 0, 1
+NPHASE = 10
+
+
+class P3MParams(C.Structure):
+    """struct p3m_params (include/p3m_b200.h)."""
+
+    _fields_ = [
+        ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32),
+        ("box", C.c_float * 3),
+        ("H", C.c_float), ("DT", C.c_float), ("G", C.c_float),
+        ("assignment", C.c_int32), ("fd_scheme", C.c_int32), ("greens_function", C.c_int32),
+        ("particle_diameter", C.c_float),
+        ("p3m", C.c_int32),
+        ("cutoff_radius", C.c_float), ("softening", C.c_float),
+        ("cloud_shape", C.c_int32), ("use_sr_table", C.c_int32),
+        ("ext_kind", C.c_int32), ("ext_center", C.c_float * 3),
+        ("ext_R", C.c_float), ("ext_M", C.c_float),
+        ("precision", C.c_int32), ("unit_roundtrip", C.c_int32),
+        ("green_zero_degenerate", C.c_int32), ("device", C.c_int32), ("timing", C.c_int32),
+    ]
+
+
+class P3MError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"p3m error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+# every symbol include/p3m_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "p3m_last_error", "p3m_version", "p3m_default_params", "p3m_create", "p3m_destroy",
+    "p3m_set_particles", "p3m_get_particles", "p3m_get_particles_f64", "p3m_num_particles",
+    "p3m_green_init", "p3m_set_green_table", "p3m_set_green_table_f64", "p3m_get_green_table",
+    "p3m_bin_sort", "p3m_deposit", "p3m_poisson", "p3m_gradient", "p3m_gather", "p3m_short_range",
+    "p3m_force", "p3m_kick", "p3m_drift", "p3m_step", "p3m_escaped", "p3m_diagnostics",
+    "p3m_get_density", "p3m_get_potential", "p3m_get_field", "p3m_get_density_f64",
+    "p3m_get_potential_f64", "p3m_set_density", "p3m_set_potential", "p3m_get_cells",
+    "p3m_get_chaining_dims", "p3m_chaining_neighbors", "p3m_get_acc_parts", "p3m_get_sr_table",
+    "p3m_get_phase_ms", "p3m_phase_name", "p3m_get_pair_counts", "p3m_launch_count", "p3m_stream",
+    "p3m_synchronize",
+]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(
+                f"{LIB_PATH} not built -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.p3m_last_error.restype = C.c_char_p
+        L.p3m_phase_name.restype = C.c_char_p
+        L.p3m_num_particles.restype = C.c_int64
+        L.p3m_launch_count.restype = C.c_int64
+        L.p3m_stream.restype = C.c_void_p
+        for name in ("p3m_num_particles", "p3m_launch_count", "p3m_stream", "p3m_destroy",
+                     "p3m_synchronize", "p3m_green_init", "p3m_bin_sort", "p3m_deposit", "p3m_poisson",
+                     "p3m_gradient", "p3m_gather", "p3m_short_range", "p3m_force", "p3m_drift"):
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.p3m_kick.argtypes = [C.c_void_p, C.c_float]
+        L.p3m_step.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.p3m_set_particles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+        for name in ("p3m_get_particles", "p3m_get_particles_f64"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        for name in ("p3m_set_green_table", "p3m_set_green_table_f64", "p3m_get_green_table",
+                     "p3m_get_density", "p3m_get_potential", "p3m_get_field", "p3m_get_density_f64",
+                     "p3m_get_potential_f64", "p3m_set_density", "p3m_set_potential", "p3m_diagnostics",
+                     "p3m_get_sr_table", "p3m_get_chaining_dims", "p3m_escaped"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
+        L.p3m_get_cells.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.p3m_get_acc_parts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.p3m_get_pair_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.p3m_get_phase_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.p3m_chaining_neighbors.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise P3MError(rc, lib().p3m_last_error().decode(errors="replace"))
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def default_params() -> P3MParams:
+    p = P3MParams()
+    lib().p3m_default_params(C.byref(p))
+    return p
+
+
+def chaining_neighbors(dims, cell):
+    dims = np.ascontiguousarray(dims, np.int32)
+    out = np.empty(14, np.int32)
+    _check(lib().p3m_chaining_neighbors(_p(dims), int(cell), _p(out)))
+    return out
+
+
+class Context:
+    """One p3m_ctx.  Thin: every method is one C-ABI call on host numpy buffers."""
+
+    def __init__(self, params: P3MParams):
+        self._h = C.c_void_p()
+        self.params = params
+        _check(lib().p3m_create(C.byref(params), C.byref(self._h)))
+        self.M = params.nx * params.ny * params.nz
+        self.shape = (params.nz, params.ny, params.nx)
+
+    def close(self):
+        if self._h:
+            lib().p3m_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def n(self):
+        return int(lib().p3m_num_particles(self._h))
+
+    def set_particles(self, pos, vel, mass, units=UNITS_ORIGINAL):
+        pos = np.ascontiguousarray(pos, np.float32)
+        mass = np.ascontiguousarray(mass, np.float32)
+        vel = None if vel is None else np.ascontiguousarray(vel, np.float32)
+        n = mass.shape[0]
+        assert pos.size == 3 * n and (vel is None or vel.size == 3 * n)
+        _check(lib().p3m_set_particles(self._h, _p(pos), _p(vel), _p(mass), n, units))
+
+    def get_particles(self, units=UNITS_CODE, f64=False, want=("pos", "vel", "acc")):
+        n = self.n
+        dt = np.float64 if f64 else np.float32
+        out = {k: (np.empty((n, 3), dt) if k in want else None) for k in ("pos", "vel", "acc")}
+        fn = lib().p3m_get_particles_f64 if f64 else lib().p3m_get_particles
+        _check(fn(self._h, _p(out["pos"]), _p(out["vel"]), _p(out["acc"]), units))
+        return out["pos"], out["vel"], out["acc"]
+
+    def green_init(self): _check(lib().p3m_green_init(self._h))
+
+    def set_green_table(self, table):
+        table = np.ascontiguousarray(table)
+        if table.dtype == np.float64:
+            _check(lib().p3m_set_green_table_f64(self._h, _p(table)))
+        else:
+            _check(lib().p3m_set_green_table(self._h, _p(np.ascontiguousarray(table, np.float32))))
+
+    def get_green_table(self):
+        g = np.empty(self.M, np.float64)
+        _check(lib().p3m_get_green_table(self._h, _p(g)))
+        return g.reshape(self.shape)
+
+    def bin_sort(self): _check(lib().p3m_bin_sort(self._h))
+    def deposit(self): _check(lib().p3m_deposit(self._h))
+    def poisson(self): _check(lib().p3m_poisson(self._h))
+    def gradient(self): _check(lib().p3m_gradient(self._h))
+    def gather(self): _check(lib().p3m_gather(self._h))
+    def short_range(self): _check(lib().p3m_short_range(self._h))
+    def force(self): _check(lib().p3m_force(self._h))
+    def kick(self, f=1.0): _check(lib().p3m_kick(self._h, float(f)))
+    def drift(self): _check(lib().p3m_drift(self._h))
+    def synchronize(self): _check(lib().p3m_synchronize(self._h))
+
+    def step(self, steps=1):
+        done = C.c_int(0)
+        _check(lib().p3m_step(self._h, int(steps), C.byref(done)))
+        return done.value
+
+    def escaped(self):
+        e = C.c_int(0)
+        _check(lib().p3m_escaped(self._h, C.byref(e)))
+        return bool(e.value)
+
+    def diagnostics(self):
+        d = np.zeros(11, np.float64)
+        _check(lib().p3m_diagnostics(self._h, _p(d)))
+        return d
+
+    def _mesh(self, fn, dt, comps=1):
+        a = np.empty(self.M * comps, dt)
+        _check(fn(self._h, _p(a)))
+        return a.reshape(self.shape + ((comps,) if comps > 1 else ()))
+
+    def density(self, f64=False):
+        return self._mesh(lib().p3m_get_density_f64 if f64 else lib().p3m_get_density,
+                          np.float64 if f64 else np.float32)
+
+    def potential(self, f64=False):
+        return self._mesh(lib().p3m_get_potential_f64 if f64 else lib().p3m_get_potential,
+                          np.float64 if f64 else np.float32)
+
+    def field(self):
+        return self._mesh(lib().p3m_get_field, np.float32, 3)
+
+    def set_density(self, rho):
+        _check(lib().p3m_set_density(self._h, _p(np.ascontiguousarray(rho, np.float32))))
+
+    def set_potential(self, phi):
+        _check(lib().p3m_set_potential(self._h, _p(np.ascontiguousarray(phi, np.float32))))
+
+    def cells(self):
+        n = self.n
+        mc = np.empty(n, np.int32); cc = np.empty(n, np.int32); order = np.empty(n, np.int32)
+        _check(lib().p3m_get_cells(self._h, _p(mc), _p(cc), _p(order)))
+        return mc, cc, order
+
+    def chaining_dims(self):
+        d = np.zeros(3, np.int32)
+        _check(lib().p3m_get_chaining_dims(self._h, _p(d)))
+        return d
+
+    def acc_parts(self):
+        n = self.n
+        pm = np.empty((n, 3), np.float64); sr = np.empty((n, 3), np.float64)
+        _check(lib().p3m_get_acc_parts(self._h, _p(pm), _p(sr)))
+        return pm, sr
+
+    def sr_table(self):
+        t = np.empty(500, np.float64)
+        _check(lib().p3m_get_sr_table(self._h, _p(t)))
+        return t
+
+    def phase_ms(self, reset=False):
+        ms = np.zeros(NPHASE, np.float32)
+        _check(lib().p3m_get_phase_ms(self._h, _p(ms), int(reset)))
+        return {lib().p3m_phase_name(i).decode(): float(ms[i]) for i in range(NPHASE)}
+
+    def pair_counts(self):
+        a = C.c_uint64(0); b = C.c_uint64(0)
+        _check(lib().p3m_get_pair_counts(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    @property
+    def launches(self):
+        return int(lib().p3m_launch_count(self._h))
+
+    @property
+    def stream(self):
+        return lib().p3m_stream(self._h)

@@ -1,0 +1,314 @@
+// binsort.cu -- particle storage, unit conversion on upload/download, cell binning and the z-order
+// cell sort.
+//
+// Replaces: the vector<Particle> copy in PMMethod::PMMethod (source/pmMethod.cpp:57-59),
+// stateToCodeUnits / massToCodeUnits (source/unitConversions.cpp:23-71), and
+// ChainingMesh::fill / fillWithYSorting (source/chainingMesh.cpp:20-58) -- the linked-list insertion
+// becomes one stable radix sort on (Morton(cell), particle id) followed by a gather of the particle
+// records, so every cell is a contiguous, id-ordered slice of the particle arrays.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "ctx.cuh"
+
+namespace p3m {
+
+template <typename T>
+static int dev_alloc(T** p, size_t count) {
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  P3M_CUDA(cudaMalloc((void**)p, sizeof(T) * (count ? count : 1)));
+  return 0;
+}
+
+template <typename T>
+int alloc_particles(p3m_ctx* c, long long n) {
+  State<T>& s = Sel<T>::st(c);
+  if (n <= c->cap) return 0;
+  long long cap = n + n / 8 + 1024;
+  P3M_TRY(dev_alloc(&s.posm, cap));
+  P3M_TRY(dev_alloc(&s.posm_alt, cap));
+  P3M_TRY(dev_alloc(&s.vel, cap));
+  P3M_TRY(dev_alloc(&s.vel_alt, cap));
+  P3M_TRY(dev_alloc(&s.acc, cap));
+  P3M_TRY(dev_alloc(&s.acc_sr, cap));
+  P3M_TRY(dev_alloc(&s.id, cap));
+  P3M_TRY(dev_alloc(&s.id_alt, cap));
+  P3M_TRY(dev_alloc(&s.keys, cap));
+  P3M_TRY(dev_alloc(&s.keys_alt, cap));
+  P3M_TRY(dev_alloc(&s.slots, cap));
+  P3M_TRY(dev_alloc(&s.slots_alt, cap));
+  P3M_TRY(dev_alloc(&s.pp_items, 2 * (cap / kPPTargets + ((size_t)1 << (3 * Sel<T>::g(c).mbits)) + 16)));
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, s.keys, s.keys_alt, s.slots, s.slots_alt, (int)cap, 0,
+                                  64, c->stream);
+  if (s.cub_tmp) cudaFree(s.cub_tmp);
+  s.cub_tmp = nullptr;
+  P3M_CUDA(cudaMalloc(&s.cub_tmp, tmp + 16));
+  s.cub_tmp_bytes = tmp;
+  c->cap = cap;
+  return 0;
+}
+
+// ---- upload: original units -> code units, exactly the reference's fp32 operations -----------------
+//   pos / H                       include/unitConversions.h:8-10
+//   DT * v / H                    include/unitConversions.h:15-17
+//   factor * m, factor = DT*DT*4*pi*G/(H*H*H) evaluated left to right   include/unitConversions.h:42-44
+template <typename T>
+__global__ void k_upload(const float* __restrict__ pos, const float* __restrict__ vel,
+                         const float* __restrict__ mass, long long n, int units, T H, T DT,
+                         T mass_factor, V4<T>* __restrict__ posm, V4<T>* __restrict__ velo,
+                         V4<T>* __restrict__ acc, V4<T>* __restrict__ acc_sr, int* __restrict__ id) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  T x = (T)pos[3 * i], y = (T)pos[3 * i + 1], z = (T)pos[3 * i + 2];
+  T vx = 0, vy = 0, vz = 0;
+  if (vel) vx = (T)vel[3 * i], vy = (T)vel[3 * i + 1], vz = (T)vel[3 * i + 2];
+  T m = (T)mass[i];
+  if (units == P3M_UNITS_ORIGINAL) {
+    x = x / H, y = y / H, z = z / H;
+    vx = DT * vx / H, vy = DT * vy / H, vz = DT * vz / H;
+    m = mass_factor * m;
+  }
+  posm[i] = V4<T>{x, y, z, m};
+  velo[i] = V4<T>{vx, vy, vz, 0};
+  acc[i] = V4<T>{0, 0, 0, 0};
+  acc_sr[i] = V4<T>{0, 0, 0, 0};
+  id[i] = (int)i;
+}
+
+template <typename T>
+int upload_particles(p3m_ctx* c, const float* pos, const float* vel, const float* mass, long long n,
+                     int units) {
+  P3M_TRY(alloc_particles<T>(c, n));
+  State<T>& s = Sel<T>::st(c);
+  // staging: reuse the sort scratch (keys: 8 B * cap >= 3 floats/particle? no -> dedicated alloc)
+  float* stage = nullptr;
+  P3M_CUDA(cudaMallocAsync((void**)&stage, sizeof(float) * 7 * (size_t)(n ? n : 1), c->stream));
+  P3M_CUDA(cudaMemcpyAsync(stage, pos, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+  if (vel)
+    P3M_CUDA(cudaMemcpyAsync(stage + 3 * n, vel, sizeof(float) * 3 * n, cudaMemcpyHostToDevice,
+                             c->stream));
+  P3M_CUDA(cudaMemcpyAsync(stage + 6 * n, mass, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+  const Geom<T>& g = Sel<T>::g(c);
+  T mf = c->f64 ? (T)c->mass_factor64 : (T)c->mass_factor32;
+  if (n > 0) {
+    k_upload<T><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+        stage, vel ? stage + 3 * n : nullptr, stage + 6 * n, n, units, g.H, g.DT, mf, s.posm, s.vel,
+        s.acc, s.acc_sr, s.id);
+    P3M_LAUNCH_CHECK(c);
+  }
+  P3M_CUDA(cudaFreeAsync(stage, c->stream));
+  c->n = n;
+  c->have_particles = true;
+  c->sorted = false;
+  return 0;
+}
+
+// ---- download: scatter back to original particle order ---------------------------------------------
+//   H * pos, H * v / DT, H * a / (DT*DT)      include/unitConversions.h:11-13,18-20,26-28
+template <typename T, typename O>
+__global__ void k_download(const V4<T>* __restrict__ posm, const V4<T>* __restrict__ vel,
+                           const V4<T>* __restrict__ acc, const int* __restrict__ id, long long n,
+                           int units, T H, T DT, O* __restrict__ pos_o, O* __restrict__ vel_o,
+                           O* __restrict__ acc_o) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long j = id[i];
+  if (pos_o) {
+    V4<T> p = posm[i];
+    if (units == P3M_UNITS_ORIGINAL) p.x = H * p.x, p.y = H * p.y, p.z = H * p.z;
+    pos_o[3 * j] = (O)p.x, pos_o[3 * j + 1] = (O)p.y, pos_o[3 * j + 2] = (O)p.z;
+  }
+  if (vel_o) {
+    V4<T> v = vel[i];
+    if (units == P3M_UNITS_ORIGINAL) v.x = H * v.x / DT, v.y = H * v.y / DT, v.z = H * v.z / DT;
+    vel_o[3 * j] = (O)v.x, vel_o[3 * j + 1] = (O)v.y, vel_o[3 * j + 2] = (O)v.z;
+  }
+  if (acc_o) {
+    V4<T> a = acc[i];
+    if (units == P3M_UNITS_ORIGINAL)
+      a.x = H * a.x / (DT * DT), a.y = H * a.y / (DT * DT), a.z = H * a.z / (DT * DT);
+    acc_o[3 * j] = (O)a.x, acc_o[3 * j + 1] = (O)a.y, acc_o[3 * j + 2] = (O)a.z;
+  }
+}
+
+template <typename T, typename O>
+int download_particles(p3m_ctx* c, O* pos, O* vel, O* acc, int units) {
+  State<T>& s = Sel<T>::st(c);
+  const Geom<T>& g = Sel<T>::g(c);
+  long long n = c->n;
+  if (n == 0) return 0;
+  O* stage = nullptr;
+  P3M_CUDA(cudaMallocAsync((void**)&stage, sizeof(O) * 9 * (size_t)n, c->stream));
+  k_download<T, O><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+      s.posm, s.vel, s.acc, s.id, n, units, g.H, g.DT, pos ? stage : nullptr,
+      vel ? stage + 3 * n : nullptr, acc ? stage + 6 * n : nullptr);
+  P3M_LAUNCH_CHECK(c);
+  if (pos) P3M_CUDA(cudaMemcpyAsync(pos, stage, sizeof(O) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+  if (vel)
+    P3M_CUDA(cudaMemcpyAsync(vel, stage + 3 * n, sizeof(O) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+  if (acc)
+    P3M_CUDA(cudaMemcpyAsync(acc, stage + 6 * n, sizeof(O) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+  P3M_CUDA(cudaFreeAsync(stage, c->stream));
+  P3M_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---- A0: sort keys ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_keys(const V4<T>* __restrict__ posm, const int* __restrict__ id, long long n,
+                       Geom<T> g, uint64_t* __restrict__ keys, uint32_t* __restrict__ slots,
+                       int* __restrict__ flags) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  V4<T> p = posm[i];
+  int cx, cy, cz;
+  bool inside;
+  bin_cell(g, p.x, p.y, p.z, cx, cy, cz, inside);
+  if (!inside) flags[1] = 1;
+  uint64_t m = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+  keys[i] = (m << g.idbits) | (uint64_t)(uint32_t)id[i];
+  slots[i] = (uint32_t)i;
+}
+
+template <typename T>
+__global__ void k_permute(const uint32_t* __restrict__ slots, long long n,
+                          const V4<T>* __restrict__ posm, const V4<T>* __restrict__ vel,
+                          const int* __restrict__ id, V4<T>* __restrict__ posm_o,
+                          V4<T>* __restrict__ vel_o, int* __restrict__ id_o) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s = slots[i];
+  posm_o[i] = posm[s];
+  vel_o[i] = vel[s];
+  id_o[i] = id[s];
+}
+
+// cell_start[c] = first sorted slot whose cell code is >= c (lower bound), c in [0, ncells]
+__global__ void k_cell_start(const uint64_t* __restrict__ keys, long long n, int idbits,
+                             long long ncells, int* __restrict__ cell_start) {
+  long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (c > ncells) return;
+  const uint64_t target = (uint64_t)c << idbits;
+  long long lo = 0, hi = n;
+  while (lo < hi) {
+    long long mid = (lo + hi) >> 1;
+    if (keys[mid] < target)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  cell_start[c] = (int)lo;
+}
+
+template <typename T>
+int bin_sort(p3m_ctx* c) {
+  if (!c->have_particles) return fail(P3M_ESTATE, "p3m_bin_sort: no particles set");
+  State<T>& s = Sel<T>::st(c);
+  Geom<T>& g = Sel<T>::g(c);
+  const long long n = c->n;
+  int idbits = 1;
+  while ((1LL << idbits) < n) ++idbits;
+  g.idbits = idbits;
+  const long long ncells = 1LL << (3 * g.mbits);
+  phase_begin(c, PH_BINSORT);
+  if (n > 0) {
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    k_keys<T><<<blocks, 256, 0, c->stream>>>(s.posm, s.id, n, g, s.keys, s.slots, s.flags);
+    P3M_LAUNCH_CHECK(c);
+    size_t tmp = s.cub_tmp_bytes;
+    P3M_CUDA(cub::DeviceRadixSort::SortPairs(s.cub_tmp, tmp, s.keys, s.keys_alt, s.slots, s.slots_alt,
+                                             (int)n, 0, idbits + 3 * g.mbits, c->stream));
+    c->launches += (idbits + 3 * g.mbits + 7) / 8 + 1;
+    k_permute<T><<<blocks, 256, 0, c->stream>>>(s.slots_alt, n, s.posm, s.vel, s.id, s.posm_alt,
+                                                s.vel_alt, s.id_alt);
+    P3M_LAUNCH_CHECK(c);
+    std::swap(s.posm, s.posm_alt);
+    std::swap(s.vel, s.vel_alt);
+    std::swap(s.id, s.id_alt);
+  }
+  k_cell_start<<<(unsigned)((ncells + 1 + 255) / 256), 256, 0, c->stream>>>(s.keys_alt, n, idbits,
+                                                                           ncells, s.cell_start);
+  P3M_LAUNCH_CHECK(c);
+  phase_end(c, PH_BINSORT);
+  c->sorted = true;
+  return 0;
+}
+
+// ---- test / diagnostics readback: the reference's own flat indices -----------------------------------
+template <typename T>
+__global__ void k_cells_out(const V4<T>* __restrict__ posm, const int* __restrict__ id, long long n,
+                            Geom<T> g, int* __restrict__ mesh_cell, int* __restrict__ chain_cell,
+                            int* __restrict__ order) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  V4<T> p = posm[i];
+  int j = id[i];
+  if (mesh_cell) {
+    // (int)pos, flat = x + y*Nx + z*Nx*Ny   source/pmMethod.cpp:250-252, include/grid.h:52-54
+    int x = (int)p.x, y = (int)p.y, z = (int)p.z;
+    mesh_cell[j] = x + y * g.nx + z * g.nx * g.ny;
+  }
+  if (chain_cell) {
+    int cc = -1;
+    if (g.p3m) {
+      // source/chainingMesh.cpp:25-29,79-84
+      int cx = (int)(p.x / g.hcx), cy = (int)(p.y / g.hcy), cz = (int)(p.z / g.hcz);
+      if (!(cx < 0 || cy < 0 || cz < 0 || cx >= g.mx || cy >= g.my || cz >= g.mz))
+        cc = cx + cy * g.mx + cz * g.mx * g.my;
+    }
+    chain_cell[j] = cc;
+  }
+  if (order) order[i] = j;
+}
+
+template <typename T>
+int get_cells(p3m_ctx* c, int32_t* mesh_cell, int32_t* chain_cell, int32_t* order) {
+  State<T>& s = Sel<T>::st(c);
+  const long long n = c->n;
+  if (n == 0) return 0;
+  int* stage = nullptr;
+  P3M_CUDA(cudaMallocAsync((void**)&stage, sizeof(int) * 3 * (size_t)n, c->stream));
+  k_cells_out<T><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+      s.posm, s.id, n, Sel<T>::g(c), mesh_cell ? stage : nullptr, chain_cell ? stage + n : nullptr,
+      order ? stage + 2 * n : nullptr);
+  P3M_LAUNCH_CHECK(c);
+  if (mesh_cell)
+    P3M_CUDA(cudaMemcpyAsync(mesh_cell, stage, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+  if (chain_cell)
+    P3M_CUDA(cudaMemcpyAsync(chain_cell, stage + n, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+  if (order)
+    P3M_CUDA(cudaMemcpyAsync(order, stage + 2 * n, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+  P3M_CUDA(cudaFreeAsync(stage, c->stream));
+  P3M_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+template <typename T>
+void free_state(p3m_ctx* c) {
+  State<T>& s = Sel<T>::st(c);
+  void* ptrs[] = {s.posm,   s.posm_alt,  s.vel,      s.vel_alt,  s.acc,        s.acc_sr,  s.id,
+                  s.id_alt, s.keys,      s.keys_alt, s.slots,    s.slots_alt,  s.cub_tmp, s.cell_start,
+                  s.density, s.potential, s.spectrum, s.green,    s.field,      s.sr_table, s.pp_items,
+                  s.pp_counters, s.pair_counts, s.flags, s.diag};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (s.plans) {
+    cufftDestroy(s.plan_fwd);
+    cufftDestroy(s.plan_inv);
+  }
+  s = State<T>();
+}
+
+#define INST(T)                                                                                  \
+  template int alloc_particles<T>(p3m_ctx*, long long);                                          \
+  template int upload_particles<T>(p3m_ctx*, const float*, const float*, const float*, long long, int); \
+  template int download_particles<T, float>(p3m_ctx*, float*, float*, float*, int);              \
+  template int download_particles<T, double>(p3m_ctx*, double*, double*, double*, int);          \
+  template int bin_sort<T>(p3m_ctx*);                                                            \
+  template int get_cells<T>(p3m_ctx*, int32_t*, int32_t*, int32_t*);                             \
+  template void free_state<T>(p3m_ctx*);
+INST(float)
+INST(double)
+
+}  // namespace p3m

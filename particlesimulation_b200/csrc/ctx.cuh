@@ -1,0 +1,143 @@
+// ctx.cuh -- the opaque context behind include/p3m_b200.h.
+#pragma once
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace p3m {
+
+struct PhaseTimer {
+  cudaEvent_t a[P3M_NPHASE], b[P3M_NPHASE];
+  float acc_ms[P3M_NPHASE];
+  bool pending[P3M_NPHASE];
+};
+
+template <typename T>
+struct State {
+  using cplx = typename CufftTypes<T>::cplx;
+  // particles, sorted order (double-buffered for the permutation)
+  V4<T>*posm = nullptr, *posm_alt = nullptr;
+  V4<T>*vel = nullptr, *vel_alt = nullptr;
+  V4<T>* acc = nullptr;     // total acceleration (mesh + short range), code units
+  V4<T>* acc_sr = nullptr;  // short-range part alone (diagnostics / parity tests)
+  int *id = nullptr, *id_alt = nullptr;
+  // sort scratch
+  uint64_t *keys = nullptr, *keys_alt = nullptr;
+  uint32_t *slots = nullptr, *slots_alt = nullptr;
+  void* cub_tmp = nullptr;
+  size_t cub_tmp_bytes = 0;
+  int* cell_start = nullptr;  // (1 << 3*mbits) + 1 entries
+  // meshes
+  T* density = nullptr;    // M
+  T* potential = nullptr;  // M
+  cplx* spectrum = nullptr;  // (nx/2+1)*ny*nz
+  T* green = nullptr;        // (nx/2+1)*ny*nz, symmetrised, includes 1/M
+  T* field = nullptr;        // 3M (only after p3m_gradient)
+  // short range
+  T* sr_table = nullptr;  // 2*kSRTable: (F[t], F[t+1]-F[t]) pairs; entry 499 = (0,0)
+  int* pp_items = nullptr;     // (cell, first target) pairs for the tiled kernel
+  int* pp_counters = nullptr;  // [0] items, [1] next item, [2] flags
+  unsigned long long* pair_counts = nullptr;  // [0] checked, [1] in range
+  int* flags = nullptr;    // [0] escaped, [1] out-of-mesh particles seen
+  double* diag = nullptr;  // 16 doubles
+  cufftHandle plan_fwd = 0, plan_inv = 0;
+  bool plans = false;
+};
+
+}  // namespace p3m
+
+struct p3m_ctx {
+  p3m_params prm;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool f64 = false;
+  long long n = 0;        // particles
+  long long cap = 0;      // allocated particle capacity
+  bool have_particles = false, have_green = false, sorted = false, have_field = false;
+  bool have_density = false, have_potential = false;
+  long long launches = 0;
+  int steps_since_sort = 0;
+  p3m::Geom<float> g32;
+  p3m::Geom<double> g64;
+  p3m::SRParams<float> sr32;
+  p3m::SRParams<double> sr64;
+  p3m::State<float> s32;
+  p3m::State<double> s64;
+  std::vector<double> sr_table_host;  // 500 entries, reference layout
+  float mass_factor32 = 0;
+  double mass_factor64 = 0;
+  int num_sms = 148;
+  p3m::PhaseTimer timer;
+  bool timing = false;
+  int count_pairs = 0;
+};
+
+namespace p3m {
+
+template <typename T>
+struct Sel;
+template <>
+struct Sel<float> {
+  static State<float>& st(p3m_ctx* c) { return c->s32; }
+  static Geom<float>& g(p3m_ctx* c) { return c->g32; }
+  static SRParams<float>& sr(p3m_ctx* c) { return c->sr32; }
+};
+template <>
+struct Sel<double> {
+  static State<double>& st(p3m_ctx* c) { return c->s64; }
+  static Geom<double>& g(p3m_ctx* c) { return c->g64; }
+  static SRParams<double>& sr(p3m_ctx* c) { return c->sr64; }
+};
+
+// phase ids (p3m_get_phase_ms)
+enum Phase {
+  PH_BINSORT = 0,
+  PH_DEPOSIT,
+  PH_FFT_FWD,
+  PH_MULTIPLY,
+  PH_FFT_INV,
+  PH_GATHER,
+  PH_SHORT_RANGE,
+  PH_INTEGRATE,
+  PH_GRADIENT,
+  PH_COMM
+};
+
+void phase_begin(p3m_ctx* c, int ph);
+void phase_end(p3m_ctx* c, int ph);
+
+// implemented one per .cu file, templated on the arithmetic type
+template <typename T> int alloc_particles(p3m_ctx* c, long long n);
+template <typename T> int alloc_meshes(p3m_ctx* c);
+template <typename T> void free_state(p3m_ctx* c);
+template <typename T> int upload_particles(p3m_ctx* c, const float* pos, const float* vel, const float* mass, long long n, int units);
+template <typename T, typename O> int download_particles(p3m_ctx* c, O* pos, O* vel, O* acc, int units);
+template <typename T> int bin_sort(p3m_ctx* c);
+template <typename T> int deposit(p3m_ctx* c);
+template <typename T> int green_init(p3m_ctx* c);
+template <typename T, typename I> int green_set(p3m_ctx* c, const I* full);
+template <typename T> int green_get(p3m_ctx* c, double* full);
+template <typename T> int poisson(p3m_ctx* c);
+template <typename T> int gradient(p3m_ctx* c);
+template <typename T> int gather(p3m_ctx* c);
+template <typename T> int short_range(p3m_ctx* c);
+template <typename T> int sr_table_upload(p3m_ctx* c);
+template <typename T> int kick(p3m_ctx* c, double f);
+template <typename T> int drift(p3m_ctx* c);
+template <typename T> int diagnostics(p3m_ctx* c, double* out);
+template <typename T> int escaped_now(p3m_ctx* c, int* escaped);
+template <typename T> int get_cells(p3m_ctx* c, int32_t* mesh_cell, int32_t* chain_cell, int32_t* order);
+template <typename T> int get_acc_parts(p3m_ctx* c, double* acc_pm, double* acc_sr);
+template <typename T, typename O> int get_mesh(p3m_ctx* c, const T* dev, O* out, long long count);
+template <typename T, typename I> int set_mesh(p3m_ctx* c, T* dev, const I* in, long long count);
+
+#define P3M_DISPATCH(c, fn, ...) ((c)->f64 ? fn<double>((c), ##__VA_ARGS__) : fn<float>((c), ##__VA_ARGS__))
+
+#define P3M_LAUNCH_CHECK(c)                   \
+  do {                                        \
+    (c)->launches++;                          \
+    P3M_CUDA(cudaGetLastError());             \
+  } while (0)
+
+}  // namespace p3m

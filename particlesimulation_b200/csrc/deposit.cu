@@ -1,0 +1,231 @@
+// deposit.cu -- A1: mass assignment, PMMethod::spreadMass + Grid::assignDensity / clearDensity
+// (source/pmMethod.cpp:200-277, source/grid.cpp:28-36).
+//
+// The reference takes one std::mutex per touched cell (27 lock/unlock pairs per TSC particle); its
+// CUDA mirror issues 27 global float atomics per particle (source/PMMethodGPU.cu:312-336).  Here the
+// particles arrive cell-sorted, so a WARP owns a run of consecutive particles and accumulates them
+// into a private shared-memory tile (the mesh footprint of one aligned block of binning cells):
+//   * sm_100a has no native shared-memory float add (atomicAdd on __shared__ float compiles to an
+//     ATOMS.CAST.SPIN loop), so the tile is updated with plain LDS/FADD/STS; exclusivity inside the
+//     warp is established per batch of 32 particles with match.any on the particle's base cell:
+//       - all lanes in one cell (dense cores): the 27 contributions are summed across the warp with
+//         shuffles and written once (warp-aggregated);
+//       - otherwise lanes sharing a cell take turns (rank rounds); for one stencil point, distinct base
+//         cells mean distinct addresses, so each round is conflict free;
+//   * the tile is flushed once per segment with native REDG.ADD (fp32 and fp64) to the global mesh,
+//     skipping zeros;
+//   * runs too short to amortise a tile (sparse outskirts) go straight to global REDG.
+// Algorithmic HBM traffic: 16 B/particle read + 4 B/cell written (+ 4 B/cell memset).
+#include "ctx.cuh"
+#include "stencil.cuh"
+
+namespace p3m {
+
+template <typename T, int K>
+__device__ __forceinline__ void deposit_direct(const Stencil<T, K>& s, const Geom<T>& g,
+                                               T* __restrict__ density) {
+#pragma unroll
+  for (int a = 0; a < K; ++a) {
+    const T t1 = s.pref * s.wx[a];
+#pragma unroll
+    for (int b = 0; b < K; ++b) {
+      const T t2 = t1 * s.wy[b];
+#pragma unroll
+      for (int cc = 0; cc < K; ++cc) {
+        const T t3 = t2 * s.wz[cc];
+        // Grid::getIndx, unwrapped (include/grid.h:52-54)
+        long long flat = (long long)(s.x0 + a) + (long long)(s.y0 + b) * g.nx +
+                         (long long)(s.z0 + cc) * g.nx * g.ny;
+        if (flat >= 0 && flat < g.M) atomicAdd(&density[flat], t3);
+      }
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T, int K>
+__global__ void __launch_bounds__(256)
+k_deposit(const V4<T>* __restrict__ posm, long long n, int chunk, const int* __restrict__ cell_start,
+          Geom<T> g, T* __restrict__ density) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int tile_cap = g.tex * g.tey * g.tez;
+  T* tile = reinterpret_cast<T*>(smem_raw) + (size_t)wib * tile_cap;
+  const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+  long long cur = warp_id * chunk;
+  const long long chunk_end = min(n, cur + (long long)chunk);
+  const long long ncells = 1LL << (3 * g.mbits);
+  const int bs3 = 3 * g.bshift;
+
+  while (cur < chunk_end) {  // warp-uniform loop over the tile segments of this chunk
+    const V4<T> p0 = posm[cur];
+    int cx, cy, cz;
+    bool inside;
+    bin_cell(g, p0.x, p0.y, p0.z, cx, cy, cz, inside);
+    const uint32_t blk = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) >> bs3;
+    long long blk_end_cell = ((long long)blk + 1) << bs3;
+    if (blk_end_cell > ncells) blk_end_cell = ncells;
+    long long seg_end = min(chunk_end, (long long)cell_start[blk_end_cell]);
+    if (seg_end <= cur) seg_end = cur + 1;
+    const int count = (int)(seg_end - cur);
+
+    if (count < g.tile_min) {
+      const long long i = cur + lane;
+      if (i < seg_end) {
+        const V4<T> p = posm[i];
+        const Stencil<T, K> s = make_stencil<T, K>(p.x, p.y, p.z, p.w);
+        deposit_direct<T, K>(s, g, density);
+      }
+      cur = seg_end;
+      continue;
+    }
+
+    int lo[3], ext[3];
+    tile_box(g, (int)compact3(blk), (int)compact3(blk >> 1), (int)compact3(blk >> 2), lo, ext);
+    const int elems = ext[0] * ext[1] * ext[2];
+    for (int e = lane; e < elems; e += 32) tile[e] = T(0);
+    __syncwarp();
+
+    for (long long b0 = cur; b0 < seg_end; b0 += 32) {
+      const long long i = b0 + lane;
+      const bool valid = i < seg_end;
+      Stencil<T, K> s;
+      int li = -1 - lane;
+      bool fits = false;
+      if (valid) {
+        const V4<T> p = posm[i];
+        s = make_stencil<T, K>(p.x, p.y, p.z, p.w);
+        const int rx = s.x0 - lo[0], ry = s.y0 - lo[1], rz = s.z0 - lo[2];
+        fits = rx >= 0 && ry >= 0 && rz >= 0 && rx + K <= ext[0] && ry + K <= ext[1] &&
+               rz + K <= ext[2];
+        if (fits)
+          li = (rz * ext[1] + ry) * ext[0] + rx;
+        else
+          deposit_direct<T, K>(s, g, density);  // does not fit the tile (rounding slop / stray)
+      }
+      const unsigned fmask = __ballot_sync(0xffffffffu, fits);
+      if (fmask == 0) continue;
+      const int leader = __ffs(fmask) - 1;
+      const int li_lead = __shfl_sync(0xffffffffu, li, leader);
+      const bool uniform = __all_sync(0xffffffffu, !fits || li == li_lead) && __popc(fmask) >= 8;
+      if (uniform) {
+        // warp-aggregated: one cell for the whole batch
+        T mine = T(0);
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < K; ++a) {
+          const T t1 = fits ? s.pref * s.wx[a] : T(0);
+#pragma unroll
+          for (int b = 0; b < K; ++b) {
+            const T t2 = fits ? t1 * s.wy[b] : T(0);
+#pragma unroll
+            for (int cc = 0; cc < K; ++cc, ++q) {
+              const T t3 = fits ? t2 * s.wz[cc] : T(0);
+              const T tot = warp_sum<T>(t3);
+              if (lane == q) mine = tot;
+            }
+          }
+        }
+        if (lane < K * K * K) {
+          const int a = lane / (K * K), b = (lane / K) % K, cc = lane % K;
+          tile[li_lead + (cc * ext[1] + b) * ext[0] + a] += mine;
+        }
+        __syncwarp();
+      } else {
+        const unsigned grp = __match_any_sync(0xffffffffu, li);
+        const int rank = __popc(grp & ((1u << lane) - 1u));
+        const int maxrank = __reduce_max_sync(0xffffffffu, fits ? rank : 0);
+        for (int r = 0; r <= maxrank; ++r) {
+          const bool act = fits && rank == r;
+#pragma unroll
+          for (int a = 0; a < K; ++a) {
+            const T t1 = s.pref * s.wx[a];
+#pragma unroll
+            for (int b = 0; b < K; ++b) {
+              const T t2 = t1 * s.wy[b];
+#pragma unroll
+              for (int cc = 0; cc < K; ++cc) {
+                if (act) tile[li + (cc * ext[1] + b) * ext[0] + a] += t2 * s.wz[cc];
+                __syncwarp();  // orders the RMW of different lanes on overlapping stencils
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+
+    // flush: native REDG.ADD to the global mesh, zeros skipped
+    const float inv0 = 1.0f / (float)ext[0], inv1 = 1.0f / (float)ext[1];
+    for (int e = lane; e < elems; e += 32) {
+      const T v = tile[e];
+      if (v != T(0)) {
+        const int q = fast_div(e, ext[0], inv0);
+        const int ix = e - q * ext[0];
+        const int iz = fast_div(q, ext[1], inv1);
+        const int iy = q - iz * ext[1];
+        long long flat = (long long)(lo[0] + ix) + (long long)(lo[1] + iy) * g.nx +
+                         (long long)(lo[2] + iz) * g.nx * g.ny;
+        if (flat >= 0 && flat < g.M) atomicAdd(&density[flat], v);
+      }
+    }
+    __syncwarp();
+    cur = seg_end;
+  }
+}
+
+template <typename T, int K>
+static int launch_deposit(p3m_ctx* c) {
+  State<T>& s = Sel<T>::st(c);
+  const Geom<T>& g = Sel<T>::g(c);
+  const long long n = c->n;
+  // chunk: enough warps to fill the machine for small N, kDepositChunk for large N
+  long long want = (n + (long long)c->num_sms * 64 - 1) / ((long long)c->num_sms * 64);
+  int chunk = (int)((want + 31) / 32 * 32);
+  if (chunk < 64) chunk = 64;
+  if (chunk > kDepositChunk) chunk = kDepositChunk;
+  const long long warps = (n + chunk - 1) / chunk;
+  const int wpb = 8;
+  const size_t smem = (size_t)wpb * g.tex * g.tey * g.tez * sizeof(T);
+  auto kern = k_deposit<T, K>;
+  P3M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, smem, c->stream>>>(s.posm, n, chunk,
+                                                                         s.cell_start, g, s.density);
+  P3M_LAUNCH_CHECK(c);
+  return 0;
+}
+
+template <typename T>
+int deposit(p3m_ctx* c) {
+  if (!c->have_particles) return fail(P3M_ESTATE, "p3m_deposit: no particles set");
+  if (!c->sorted) return fail(P3M_ESTATE, "p3m_deposit: call p3m_bin_sort first");
+  State<T>& s = Sel<T>::st(c);
+  const Geom<T>& g = Sel<T>::g(c);
+  phase_begin(c, PH_DEPOSIT);
+  // Grid::clearDensity (source/grid.cpp:34-36)
+  P3M_CUDA(cudaMemsetAsync(s.density, 0, sizeof(T) * (size_t)g.M, c->stream));
+  c->launches++;
+  int r = 0;
+  if (c->n > 0) {
+    if (g.is == P3M_TSC)
+      r = launch_deposit<T, 3>(c);
+    else if (g.is == P3M_CIC)
+      r = launch_deposit<T, 2>(c);
+    else
+      r = launch_deposit<T, 1>(c);
+  }
+  phase_end(c, PH_DEPOSIT);
+  c->have_density = (r == 0);
+  return r;
+}
+
+template int deposit<float>(p3m_ctx*);
+template int deposit<double>(p3m_ctx*);
+
+}  // namespace p3m

@@ -1,0 +1,271 @@
+// gather.cu -- A5 + A6: PMMethod::findFieldInCells / getFieldInCell and
+// PMMethod::updateAccelerations / interpolateField (source/pmMethod.cpp:279-338, 352-390), fused.
+//
+// The reference materialises a Vec3 field mesh (12 B/cell written, then re-read at random by every
+// particle).  Here a CTA walks a run of cell-sorted particles; for each aligned block of binning cells
+// it stages the POTENTIAL tile (+ finite-difference halo) in shared memory, differences it once into an
+// E tile, and the block's particles interpolate from shared memory.  HBM traffic drops from
+// 16 B/cell + 12 B/cell + 24 B/particle to ~4 B/cell + 28 B/particle; the field mesh is never written.
+// p3m_gradient() still produces the explicit field mesh for callers of Grid::getField.
+//
+// Quirks kept: truncated base cell, field cells addressed by the UNWRAPPED flat index
+// (only the potential wraps periodically, source/grid.cpp:46-48,66-68).  Particles whose stencil leaves
+// [0,N) on some axis -- where the unwrapped index aliases into a neighbouring row -- take the exact
+// per-cell path below instead of the tile.
+#include "ctx.cuh"
+#include "stencil.cuh"
+
+namespace p3m {
+
+// -E = grad(phi) by centred differences with periodic wrap (source/pmMethod.cpp:352-371)
+template <typename T, int FD>
+__device__ __forceinline__ void field_at(const T* __restrict__ phi, const Geom<T>& g, int x, int y,
+                                         int z, T& fx, T& fy, T& fz) {
+  const long long sx = 1, sy = g.nx, sz = (long long)g.nx * g.ny;
+  auto P = [&](int a, int b, int cc) -> T {
+    return phi[wrap_idx(a, g.nx) * sx + wrap_idx(b, g.ny) * sy + wrap_idx(cc, g.nz) * sz];
+  };
+  if (FD == 1) {
+    fx = T(-0.5) * (P(x + 1, y, z) - P(x - 1, y, z));
+    fy = T(-0.5) * (P(x, y + 1, z) - P(x, y - 1, z));
+    fz = T(-0.5) * (P(x, y, z + 1) - P(x, y, z - 1));
+  } else {
+    const T k = T(-1.0) / 12;
+    fx = k * (-P(x + 2, y, z) + 8 * P(x + 1, y, z) - 8 * P(x - 1, y, z) + P(x - 2, y, z));
+    fy = k * (-P(x, y + 2, z) + 8 * P(x, y + 1, z) - 8 * P(x, y - 1, z) + P(x, y - 2, z));
+    fz = k * (-P(x, y, z + 2) + 8 * P(x, y, z + 1) - 8 * P(x, y, z - 1) + P(x, y, z - 2));
+  }
+}
+
+// exact restatement for one particle straight from global memory (any position)
+template <typename T, int K, int FD>
+__device__ __forceinline__ void gather_direct(const Stencil<T, K>& s, const Geom<T>& g,
+                                              const T* __restrict__ phi, T& ax, T& ay, T& az) {
+  const T scale = (K == 3) ? T(0.125) : T(1);
+#pragma unroll
+  for (int a = 0; a < K; ++a)
+#pragma unroll
+    for (int b = 0; b < K; ++b)
+#pragma unroll
+      for (int cc = 0; cc < K; ++cc) {
+        const T w = scale * ((s.wx[a] * s.wy[b]) * s.wz[cc]);
+        long long flat = (long long)(s.x0 + a) + (long long)(s.y0 + b) * g.nx +
+                         (long long)(s.z0 + cc) * g.nx * g.ny;
+        if (flat < 0 || flat >= g.M) continue;  // out of the arrays: undefined in the reference
+        const int x = (int)(flat % g.nx), y = (int)((flat / g.nx) % g.ny),
+                  z = (int)(flat / ((long long)g.nx * g.ny));
+        T fx, fy, fz;
+        field_at<T, FD>(phi, g, x, y, z, fx, fy, fz);
+        ax += w * fx, ay += w * fy, az += w * fz;
+      }
+}
+
+// externalField in original units -> code units (source/pmMethod.cpp:386-388,
+// source/externalFields.cpp:4-15, include/unitConversions.h:22-24)
+template <typename T>
+__device__ __forceinline__ void add_external(const Geom<T>& g, T x, T y, T z, T& ax, T& ay, T& az) {
+  if (g.ext_kind != P3M_EXT_SPH_RAD_DECR) return;
+  const T dx = g.H * x - g.ecx, dy = g.H * y - g.ecy, dz = g.H * z - g.ecz;
+  const T r = sqrt(dx * dx + dy * dy + dz * dz);
+  T gg;
+  if (r > g.eR)
+    gg = -g.G * g.eM / (r * r);
+  else
+    gg = -(g.G * g.eM / (g.eR * g.eR * g.eR)) * r * (4 - 3 * r / g.eR);
+  const T ex = gg * (dx / r), ey = gg * (dy / r), ez = gg * (dz / r);
+  ax += g.DT * g.DT * ex / g.H, ay += g.DT * g.DT * ey / g.H, az += g.DT * g.DT * ez / g.H;
+}
+
+template <typename T, int K, int FD>
+__global__ void __launch_bounds__(256)
+k_gather(const V4<T>* __restrict__ posm, long long n, int chunk, const int* __restrict__ cell_start,
+         Geom<T> g, const T* __restrict__ phi, V4<T>* __restrict__ acc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int tile_cap = g.tex * g.tey * g.tez;
+  const int pcap = (g.tex + 2 * FD) * (g.tey + 2 * FD) * (g.tez + 2 * FD);
+  T* sphi = reinterpret_cast<T*>(smem_raw);
+  T* sEx = sphi + pcap;
+  T* sEy = sEx + tile_cap;
+  T* sEz = sEy + tile_cap;
+  long long cur = (long long)blockIdx.x * chunk;
+  const long long chunk_end = min(n, cur + (long long)chunk);
+  const long long ncells = 1LL << (3 * g.mbits);
+  const int bs3 = 3 * g.bshift;
+  const T scale = (K == 3) ? T(0.125) : T(1);
+
+  while (cur < chunk_end) {  // CTA-uniform loop over tile segments
+    const V4<T> p0 = posm[cur];
+    int cx, cy, cz;
+    bool inside;
+    bin_cell(g, p0.x, p0.y, p0.z, cx, cy, cz, inside);
+    const uint32_t blk = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) >> bs3;
+    long long blk_end_cell = ((long long)blk + 1) << bs3;
+    if (blk_end_cell > ncells) blk_end_cell = ncells;
+    long long seg_end = min(chunk_end, (long long)cell_start[blk_end_cell]);
+    if (seg_end <= cur) seg_end = cur + 1;
+    const int count = (int)(seg_end - cur);
+
+    if (count < 2 * (long long)g.tile_min) {
+      for (long long i = cur + tid; i < seg_end; i += blockDim.x) {
+        const V4<T> p = posm[i];
+        const Stencil<T, K> s = make_stencil<T, K>(p.x, p.y, p.z, p.w);
+        T ax = 0, ay = 0, az = 0;
+        gather_direct<T, K, FD>(s, g, phi, ax, ay, az);
+        add_external(g, p.x, p.y, p.z, ax, ay, az);
+        acc[i] = V4<T>{ax, ay, az, 0};
+      }
+      cur = seg_end;
+      continue;
+    }
+
+    int lo[3], ext[3];
+    tile_box(g, (int)compact3(blk), (int)compact3(blk >> 1), (int)compact3(blk >> 2), lo, ext);
+    const int px = ext[0] + 2 * FD, py = ext[1] + 2 * FD, pz = ext[2] + 2 * FD;
+    const int pelems = px * py * pz, elems = ext[0] * ext[1] * ext[2];
+    {
+      const float ipx = 1.0f / (float)px, ipy = 1.0f / (float)py;
+      for (int e = tid; e < pelems; e += blockDim.x) {
+        const int q = fast_div(e, px, ipx);
+        const int ix = e - q * px;
+        const int iz = fast_div(q, py, ipy);
+        const int iy = q - iz * py;
+        const int gx = wrap_idx(lo[0] - FD + ix, g.nx), gy = wrap_idx(lo[1] - FD + iy, g.ny),
+                  gz = wrap_idx(lo[2] - FD + iz, g.nz);
+        sphi[e] = phi[(long long)gx + (long long)gy * g.nx + (long long)gz * g.nx * g.ny];
+      }
+    }
+    __syncthreads();
+    {
+      const float i0 = 1.0f / (float)ext[0], i1 = 1.0f / (float)ext[1];
+      const int sy = px, sz = px * py;
+      for (int e = tid; e < elems; e += blockDim.x) {
+        const int q = fast_div(e, ext[0], i0);
+        const int ix = e - q * ext[0];
+        const int iz = fast_div(q, ext[1], i1);
+        const int iy = q - iz * ext[1];
+        const T* c0 = sphi + (iz + FD) * sz + (iy + FD) * sy + (ix + FD);
+        T fx, fy, fz;
+        if (FD == 1) {
+          fx = T(-0.5) * (c0[1] - c0[-1]);
+          fy = T(-0.5) * (c0[sy] - c0[-sy]);
+          fz = T(-0.5) * (c0[sz] - c0[-sz]);
+        } else {
+          const T k = T(-1.0) / 12;
+          fx = k * (-c0[2] + 8 * c0[1] - 8 * c0[-1] + c0[-2]);
+          fy = k * (-c0[2 * sy] + 8 * c0[sy] - 8 * c0[-sy] + c0[-2 * sy]);
+          fz = k * (-c0[2 * sz] + 8 * c0[sz] - 8 * c0[-sz] + c0[-2 * sz]);
+        }
+        sEx[e] = fx, sEy[e] = fy, sEz[e] = fz;
+      }
+    }
+    __syncthreads();
+
+    for (long long i = cur + tid; i < seg_end; i += blockDim.x) {
+      const V4<T> p = posm[i];
+      const Stencil<T, K> s = make_stencil<T, K>(p.x, p.y, p.z, p.w);
+      const int rx = s.x0 - lo[0], ry = s.y0 - lo[1], rz = s.z0 - lo[2];
+      const bool fits = rx >= 0 && ry >= 0 && rz >= 0 && rx + K <= ext[0] && ry + K <= ext[1] &&
+                        rz + K <= ext[2] && s.x0 >= 0 && s.y0 >= 0 && s.z0 >= 0 &&
+                        s.x0 + K <= g.nx && s.y0 + K <= g.ny && s.z0 + K <= g.nz;
+      T ax = 0, ay = 0, az = 0;
+      if (fits) {
+        const int base = (rz * ext[1] + ry) * ext[0] + rx;
+#pragma unroll
+        for (int a = 0; a < K; ++a)
+#pragma unroll
+          for (int b = 0; b < K; ++b)
+#pragma unroll
+            for (int cc = 0; cc < K; ++cc) {
+              const T w = scale * ((s.wx[a] * s.wy[b]) * s.wz[cc]);
+              const int e = base + (cc * ext[1] + b) * ext[0] + a;
+              ax += w * sEx[e], ay += w * sEy[e], az += w * sEz[e];
+            }
+      } else {
+        gather_direct<T, K, FD>(s, g, phi, ax, ay, az);
+      }
+      add_external(g, p.x, p.y, p.z, ax, ay, az);
+      acc[i] = V4<T>{ax, ay, az, 0};
+    }
+    __syncthreads();
+    cur = seg_end;
+  }
+}
+
+template <typename T, int K, int FD>
+static int launch_gather(p3m_ctx* c) {
+  State<T>& s = Sel<T>::st(c);
+  const Geom<T>& g = Sel<T>::g(c);
+  const long long n = c->n;
+  long long want = (n + (long long)c->num_sms * 8 - 1) / ((long long)c->num_sms * 8);
+  int chunk = (int)((want + 255) / 256 * 256);
+  if (chunk < 256) chunk = 256;
+  if (chunk > kGatherChunk) chunk = kGatherChunk;
+  const long long blocks = (n + chunk - 1) / chunk;
+  const size_t smem = sizeof(T) * ((size_t)(g.tex + 2 * FD) * (g.tey + 2 * FD) * (g.tez + 2 * FD) +
+                                   3 * (size_t)g.tex * g.tey * g.tez);
+  auto kern = k_gather<T, K, FD>;
+  P3M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)blocks, 256, smem, c->stream>>>(s.posm, n, chunk, s.cell_start, g, s.potential,
+                                                   s.acc);
+  P3M_LAUNCH_CHECK(c);
+  return 0;
+}
+
+template <typename T>
+int gather(p3m_ctx* c) {
+  if (!c->have_particles || !c->sorted) return fail(P3M_ESTATE, "p3m_gather: particles not sorted");
+  if (!c->have_potential) return fail(P3M_ESTATE, "p3m_gather: no potential (call p3m_poisson)");
+  const Geom<T>& g = Sel<T>::g(c);
+  phase_begin(c, PH_GATHER);
+  int r = 0;
+  if (c->n > 0) {
+    const int k = g.is == P3M_TSC ? 3 : (g.is == P3M_CIC ? 2 : 1);
+    const int fd = g.fds == P3M_TWO_POINT ? 1 : 2;
+    if (k == 3 && fd == 1) r = launch_gather<T, 3, 1>(c);
+    else if (k == 3 && fd == 2) r = launch_gather<T, 3, 2>(c);
+    else if (k == 2 && fd == 1) r = launch_gather<T, 2, 1>(c);
+    else if (k == 2 && fd == 2) r = launch_gather<T, 2, 2>(c);
+    else if (k == 1 && fd == 1) r = launch_gather<T, 1, 1>(c);
+    else r = launch_gather<T, 1, 2>(c);
+  }
+  phase_end(c, PH_GATHER);
+  return r;
+}
+
+// ---- explicit field mesh (PMMethod::findFieldInCells, source/pmMethod.cpp:373-382) -----------------
+template <typename T, int FD>
+__global__ void k_gradient(const T* __restrict__ phi, Geom<T> g, T* __restrict__ field) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= g.M) return;
+  const int x = (int)(idx % g.nx), y = (int)((idx / g.nx) % g.ny),
+            z = (int)(idx / ((long long)g.nx * g.ny));
+  T fx, fy, fz;
+  field_at<T, FD>(phi, g, x, y, z, fx, fy, fz);
+  field[3 * idx] = fx, field[3 * idx + 1] = fy, field[3 * idx + 2] = fz;
+}
+
+template <typename T>
+int gradient(p3m_ctx* c) {
+  if (!c->have_potential) return fail(P3M_ESTATE, "p3m_gradient: no potential (call p3m_poisson)");
+  State<T>& s = Sel<T>::st(c);
+  const Geom<T>& g = Sel<T>::g(c);
+  if (!s.field) P3M_CUDA(cudaMalloc((void**)&s.field, sizeof(T) * 3 * (size_t)g.M));
+  phase_begin(c, PH_GRADIENT);
+  const unsigned blocks = (unsigned)((g.M + 255) / 256);
+  if (g.fds == P3M_TWO_POINT)
+    k_gradient<T, 1><<<blocks, 256, 0, c->stream>>>(s.potential, g, s.field);
+  else
+    k_gradient<T, 2><<<blocks, 256, 0, c->stream>>>(s.potential, g, s.field);
+  P3M_LAUNCH_CHECK(c);
+  phase_end(c, PH_GRADIENT);
+  c->have_field = true;
+  return 0;
+}
+
+template int gather<float>(p3m_ctx*);
+template int gather<double>(p3m_ctx*);
+template int gradient<float>(p3m_ctx*);
+template int gradient<double>(p3m_ctx*);
+
+}  // namespace p3m

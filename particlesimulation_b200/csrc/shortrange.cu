@@ -1,0 +1,359 @@
+// shortrange.cu -- A7 + A8 + A9: the chaining-mesh short-range particle-particle correction.
+//
+// Replaces P3MMethod::calculateShortRangeForces / updateSRForcesThreadJob / updateSRForces,
+// shortRangeForce(FromTable), initSRForceTable and correctAccelerations
+// (source/p3mMethod.cpp:50-57, 168-322) together with the ChainingMesh linked lists
+// (source/chainingMesh.cpp:20-84).
+//
+// The reference walks a half shell of 13 + 1 neighbour cells per cell, applies Newton's third law into
+// 13 per-particle neighbour slots (168 B of accumulators per particle) and divides by the mass at the
+// end.  Because the chaining cell is never smaller than the cutoff (M = int(box / re)), the result is
+// simply "sum over all j with |r_ij| < re"; here every TARGET gathers that sum itself from the full
+// 27-cell neighbourhood (no scatter, no atomics, no slots, bit-reproducible run to run), and the
+// acceleration mj * f(r) * r_ij is accumulated directly (the reference's  mi*mj*f / mi).
+//
+//   dense cells (>= kDenseCell particles; the Plummer core puts ~half of all particles in 8 cells):
+//     work item = (cell, 256 consecutive targets), 128 threads x 2 targets in registers; the
+//     neighbour cells' particles are streamed through a shared-memory tile and read back with
+//     broadcast LDS.128; items are generated on the device, sorted by cost (heaviest first) and
+//     pulled from an atomic queue by a persistent grid, so the O(n_cell^2) core does not serialise
+//     on a few CTAs.
+//   sparse cells: one thread per target walks its 27 cells straight from L1/L2.
+//
+// Force law (code units, G = 1/(4 pi)): table mode reproduces shortRangeForceFromTable
+// (:240-245): linear interpolation in r^2 over 500 entries, multiplied by r_ij (NOT the unit vector,
+// SURVEY Q7); the cutoff test r^2 >= re^2 (:258) is folded into the lookup by clamping xi to 499,
+// whose entry is (0, 0).  r = 0 contributes exactly 0 (F[0] = 0), so i == j needs no test.
+// FP32 pipe bound: ~19 instructions per examined pair.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <cmath>
+#include <vector>
+
+#include "ctx.cuh"
+
+namespace p3m {
+
+template <typename T>
+struct alignas(2 * sizeof(T)) V2 {
+  T x, y;
+};
+
+template <typename T>
+__device__ __forceinline__ T ref_force_dev(const SRParams<T>& sp, T r) {
+  const T G = T(0.07957747154594767);  // 1 / (4 pi)
+  const T a = sp.a;
+  if (sp.cloud == P3M_S1) {  // referenceForceS1 :194-201
+    if (r >= a) return G / (r * r);
+    const T q = r / a;
+    return G / (a * a) * (8 * r / a - 9 * r * r / (a * a) + 2 * q * q * q * q);
+  }
+  const T u = 2 * r / a;  // referenceForceS2 :203-218
+  const T u2 = u * u, u3 = u2 * u, u4 = u2 * u2, u5 = u4 * u, u6 = u3 * u3;
+  if (u <= 1) return G / (35 * a * a) * (224 * u - 224 * u3 + 70 * u4 + 48 * u5 - 21 * u6);
+  if (u <= 2)
+    return G / (35 * a * a) *
+           (12 / u2 - 224 + 896 * u - 840 * u2 + 224 * u3 + 70 * u4 - 48 * u5 + 7 * u6);
+  return G / (r * r);
+}
+
+template <typename T, bool TABLE, bool COUNT>
+__device__ __forceinline__ void pair_acc(T dx, T dy, T dz, T mj, const SRParams<T>& sp,
+                                         const V2<T>* __restrict__ tab, T& ax, T& ay, T& az,
+                                         unsigned& n_in) {
+  const T r2 = dx * dx + dy * dy + dz * dz;
+  if (COUNT) n_in += (r2 < sp.re2 && r2 > T(0)) ? 1u : 0u;
+  if (TABLE) {
+    const T xi = fmin(r2 * sp.inv_delta2, T(kSRTable - 1));
+    const int t = (int)xi;
+    const V2<T> e = tab[t];
+    const T f = mj * (e.x + (xi - (T)t) * e.y);
+    ax += f * dx, ay += f * dy, az += f * dz;
+  } else {
+    if (r2 < sp.re2 && r2 > T(0)) {  // shortRangeForce :220-238, divided by mi
+      const T r = sqrt(r2);
+      const T G = T(0.07957747154594767);
+      const T f = mj * (ref_force_dev(sp, r) - G / (r2 + sp.eps2)) / r;
+      ax += f * dx, ay += f * dy, az += f * dz;
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void load_table(const T* __restrict__ g_tab, V2<T>* s_tab) {
+  for (int t = threadIdx.x; t < kSRTable; t += blockDim.x) s_tab[t] = V2<T>{g_tab[2 * t], g_tab[2 * t + 1]};
+}
+
+// ---- work items for the dense cells ------------------------------------------------------------------
+template <typename T>
+__global__ void k_pp_items(const int* __restrict__ cell_start, Geom<T> g, int* __restrict__ items,
+                           unsigned* __restrict__ cost, int* __restrict__ counters) {
+  const long long ncells = 1LL << (3 * g.mbits);
+  long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  const int s = cell_start[c], nq = cell_start[c + 1] - s;
+  if (nq < kDenseCell) return;
+  const int cx = (int)compact3((uint32_t)c), cy = (int)compact3((uint32_t)c >> 1),
+            cz = (int)compact3((uint32_t)c >> 2);
+  long long src = 0;
+  for (int dz = -1; dz <= 1; ++dz)
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int x = cx + dx, y = cy + dy, z = cz + dz;
+        if (x < 0 || y < 0 || z < 0 || x >= g.mx || y >= g.my || z >= g.mz) continue;
+        const uint32_t qn = morton3((uint32_t)x, (uint32_t)y, (uint32_t)z);
+        src += cell_start[qn + 1] - cell_start[qn];
+      }
+  const int k = (nq + kPPTargets - 1) / kPPTargets;
+  const int base = atomicAdd(&counters[0], k);
+  for (int t = 0; t < k; ++t) {
+    items[2 * (base + t)] = (int)c;
+    items[2 * (base + t) + 1] = s + t * kPPTargets;
+    const int nt = min(kPPTargets, nq - t * kPPTargets);
+    long long w = (src * nt) >> 10;
+    cost[base + t] = (unsigned)min(w, 0xffffffffLL);
+  }
+}
+
+template <typename T, bool TABLE, bool COUNT>
+__global__ void __launch_bounds__(128)
+k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
+           const int* __restrict__ items, const unsigned* __restrict__ order,
+           int* __restrict__ counters, Geom<T> g, SRParams<T> sp, const T* __restrict__ g_tab,
+           V4<T>* __restrict__ acc, V4<T>* __restrict__ acc_sr,
+           unsigned long long* __restrict__ pair_counts) {
+  __shared__ V2<T> s_tab[kSRTable];
+  __shared__ V4<T> s_src[kPPTargets];
+  __shared__ int s_item;
+  load_table(g_tab, s_tab);
+  const int tid = threadIdx.x;
+  const int nitems = counters[0];
+  unsigned long long checked = 0, inrange = 0;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_item = atomicAdd(&counters[1], 1);
+    __syncthreads();
+    const int it = s_item;
+    if (it >= nitems) break;
+    const int item = (int)order[it];
+    const uint32_t q = (uint32_t)items[2 * item];
+    const int t0 = items[2 * item + 1];
+    const int tend = min(cell_start[q + 1], t0 + kPPTargets);
+    const int i0 = t0 + tid, i1 = t0 + 128 + tid;
+    const bool v0 = i0 < tend, v1 = i1 < tend;
+    V4<T> p0 = posm[v0 ? i0 : t0], p1 = posm[v1 ? i1 : t0];
+    T a0x = 0, a0y = 0, a0z = 0, a1x = 0, a1y = 0, a1z = 0;
+    unsigned n_in = 0;
+    const int cx = (int)compact3(q), cy = (int)compact3(q >> 1), cz = (int)compact3(q >> 2);
+    for (int dz = -1; dz <= 1; ++dz)
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int x = cx + dx, y = cy + dy, z = cz + dz;
+          if (x < 0 || y < 0 || z < 0 || x >= g.mx || y >= g.my || z >= g.mz) continue;
+          const uint32_t qn = morton3((uint32_t)x, (uint32_t)y, (uint32_t)z);
+          const int s = cell_start[qn], e = cell_start[qn + 1];
+          for (int base = s; base < e; base += kPPTargets) {
+            __syncthreads();
+            const int j0 = base + tid, j1 = base + 128 + tid;
+            if (j0 < e) s_src[tid] = posm[j0];
+            if (j1 < e) s_src[tid + 128] = posm[j1];
+            __syncthreads();
+            const int cnt = min(kPPTargets, e - base);
+            if (COUNT) checked += (unsigned long long)cnt * ((v0 ? 1 : 0) + (v1 ? 1 : 0));
+#pragma unroll 4
+            for (int j = 0; j < cnt; ++j) {
+              const V4<T> sj = s_src[j];
+              unsigned c0 = 0, c1 = 0;
+              pair_acc<T, TABLE, COUNT>(p0.x - sj.x, p0.y - sj.y, p0.z - sj.z, sj.w, sp, s_tab, a0x,
+                                        a0y, a0z, c0);
+              pair_acc<T, TABLE, COUNT>(p1.x - sj.x, p1.y - sj.y, p1.z - sj.z, sj.w, sp, s_tab, a1x,
+                                        a1y, a1z, c1);
+              if (COUNT) n_in += (v0 ? c0 : 0u) + (v1 ? c1 : 0u);
+            }
+          }
+        }
+    if (v0) {
+      acc_sr[i0] = V4<T>{a0x, a0y, a0z, 0};
+      V4<T> a = acc[i0];
+      acc[i0] = V4<T>{a.x + a0x, a.y + a0y, a.z + a0z, 0};  // correctAccelerations :55
+    }
+    if (v1) {
+      acc_sr[i1] = V4<T>{a1x, a1y, a1z, 0};
+      V4<T> a = acc[i1];
+      acc[i1] = V4<T>{a.x + a1x, a.y + a1y, a.z + a1z, 0};
+    }
+    if (COUNT) inrange += n_in;
+  }
+  if (COUNT) {
+    // self pairs are examined by the reference too (i == j returns early), so only subtract nothing
+    atomicAdd(&pair_counts[0], checked);
+    atomicAdd(&pair_counts[1], inrange);
+  }
+}
+
+template <typename T, bool TABLE, bool COUNT>
+__global__ void __launch_bounds__(128)
+k_pp_sparse(const V4<T>* __restrict__ posm, long long n, const int* __restrict__ cell_start,
+            Geom<T> g, SRParams<T> sp, const T* __restrict__ g_tab, V4<T>* __restrict__ acc,
+            V4<T>* __restrict__ acc_sr, unsigned long long* __restrict__ pair_counts) {
+  __shared__ V2<T> s_tab[kSRTable];
+  load_table(g_tab, s_tab);
+  __syncthreads();
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const V4<T> p = posm[i];
+  int cx, cy, cz;
+  bool inside;
+  bin_cell(g, p.x, p.y, p.z, cx, cy, cz, inside);
+  const uint32_t q = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+  if (cell_start[q + 1] - cell_start[q] >= kDenseCell) return;  // tiled kernel owns this cell
+  T ax = 0, ay = 0, az = 0;
+  unsigned n_in = 0;
+  unsigned long long checked = 0;
+  for (int dz = -1; dz <= 1; ++dz)
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int x = cx + dx, y = cy + dy, z = cz + dz;
+        if (x < 0 || y < 0 || z < 0 || x >= g.mx || y >= g.my || z >= g.mz) continue;
+        const uint32_t qn = morton3((uint32_t)x, (uint32_t)y, (uint32_t)z);
+        const int s = cell_start[qn], e = cell_start[qn + 1];
+        if (COUNT) checked += (unsigned long long)(e - s);
+        for (int j = s; j < e; ++j) {
+          const V4<T> sj = posm[j];
+          pair_acc<T, TABLE, COUNT>(p.x - sj.x, p.y - sj.y, p.z - sj.z, sj.w, sp, s_tab, ax, ay, az,
+                                    n_in);
+        }
+      }
+  acc_sr[i] = V4<T>{ax, ay, az, 0};
+  const V4<T> a = acc[i];
+  acc[i] = V4<T>{a.x + ax, a.y + ay, a.z + az, 0};
+  if (COUNT) {
+    atomicAdd(&pair_counts[0], checked);
+    atomicAdd(&pair_counts[1], (unsigned long long)n_in);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+// initSRForceTable (source/p3mMethod.cpp:275-294) in the context's precision, same operation order
+template <typename T>
+static void build_table_host(const p3m_ctx* c, const SRParams<T>& sp, T delta2, T eps, std::vector<T>& F) {
+  F.resize(kSRTable);
+  const T G = 1 / (4 * (T)3.14159265358979323846);
+  auto refS1 = [&](T r) -> T {
+    const T a = sp.a;
+    if (r >= a) return G / (r * r);
+    return G / (a * a) * (8 * r / a - 9 * r * r / (a * a) + 2 * std::pow(r / a, (T)4));
+  };
+  auto refS2 = [&](T r) -> T {
+    const T a = sp.a;
+    const T u = 2 * r / a;
+    if (u <= 1)
+      return G / (35 * std::pow(a, (T)2)) *
+             (224 * u - 224 * std::pow(u, (T)3) + 70 * std::pow(u, (T)4) + 48 * std::pow(u, (T)5) -
+              21 * std::pow(u, (T)6));
+    if (u <= 2)
+      return G / (35 * std::pow(a, (T)2)) *
+             (12 / std::pow(u, (T)2) - 224 + 896 * u - 840 * std::pow(u, (T)2) +
+              224 * std::pow(u, (T)3) + 70 * std::pow(u, (T)4) - 48 * std::pow(u, (T)5) +
+              7 * std::pow(u, (T)6));
+    return G / (r * r);
+  };
+  for (int i = 0; i < kSRTable; ++i) {
+    const T r2 = i * delta2;
+    const T r = std::sqrt(r2);
+    const T R = -(c->prm.cloud_shape == P3M_S1 ? refS1(r) : refS2(r));
+    const T total = -G / (r * r + eps * eps);
+    F[i] = (r == 0) ? 0 : (total - R) / std::sqrt(r * r + eps * eps);
+  }
+}
+
+template <typename T>
+int sr_table_upload(p3m_ctx* c) {
+  State<T>& s = Sel<T>::st(c);
+  SRParams<T>& sp = Sel<T>::sr(c);
+  const p3m_params& p = c->prm;
+  // code-unit lengths, source/p3mMethod.cpp:35-37,42-44
+  const T re = (T)p.cutoff_radius / (T)p.H;
+  sp.a = (T)p.particle_diameter / (T)p.H;
+  const T eps = (T)p.softening / (T)p.H;
+  const T delta2 = re * re / (kSRTable - 1);
+  sp.re2 = re * re;
+  sp.inv_delta2 = 1 / delta2;
+  sp.eps2 = eps * eps;
+  sp.use_table = p.use_sr_table;
+  sp.cloud = p.cloud_shape;
+  std::vector<T> F;
+  build_table_host<T>(c, sp, delta2, eps, F);
+  c->sr_table_host.assign(F.begin(), F.end());
+  std::vector<T> pairs(2 * kSRTable);
+  for (int t = 0; t < kSRTable - 1; ++t) pairs[2 * t] = F[t], pairs[2 * t + 1] = F[t + 1] - F[t];
+  pairs[2 * (kSRTable - 1)] = 0, pairs[2 * (kSRTable - 1) + 1] = 0;
+  P3M_CUDA(cudaMemcpyAsync(s.sr_table, pairs.data(), sizeof(T) * 2 * kSRTable, cudaMemcpyHostToDevice,
+                           c->stream));
+  P3M_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+template <typename T>
+__global__ void k_iota_zero(unsigned* idx, unsigned* cost, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) idx[i] = (unsigned)i, cost[i] = 0u;
+}
+
+template <typename T, bool TABLE, bool COUNT>
+static int run_pp(p3m_ctx* c) {
+  State<T>& s = Sel<T>::st(c);
+  const Geom<T>& g = Sel<T>::g(c);
+  const SRParams<T>& sp = Sel<T>::sr(c);
+  const long long n = c->n;
+  const long long ncells = 1LL << (3 * g.mbits);
+  // upper bound on dense-cell work items: every dense cell holds >= kDenseCell particles
+  long long max_items = n / kPPTargets + (ncells < n / kDenseCell ? ncells : n / kDenseCell) + 16;
+  unsigned* cost = reinterpret_cast<unsigned*>(s.keys);          // 8 B * cap available
+  unsigned* cost_sorted = reinterpret_cast<unsigned*>(s.keys_alt);
+  unsigned* idx = s.slots;
+  unsigned* order = s.slots_alt;
+  if (max_items > c->cap) max_items = c->cap;
+  P3M_CUDA(cudaMemsetAsync(s.pp_counters, 0, sizeof(int) * 8, c->stream));
+  if (COUNT) P3M_CUDA(cudaMemsetAsync(s.pair_counts, 0, sizeof(unsigned long long) * 2, c->stream));
+  k_iota_zero<T><<<(unsigned)((max_items + 255) / 256), 256, 0, c->stream>>>(idx, cost, max_items);
+  P3M_LAUNCH_CHECK(c);
+  k_pp_items<T><<<(unsigned)((ncells + 255) / 256), 256, 0, c->stream>>>(s.cell_start, g, s.pp_items,
+                                                                         cost, s.pp_counters);
+  P3M_LAUNCH_CHECK(c);
+  size_t tmp = s.cub_tmp_bytes;
+  P3M_CUDA(cub::DeviceRadixSort::SortPairsDescending(s.cub_tmp, tmp, cost, cost_sorted, idx, order,
+                                                     (int)max_items, 0, 32, c->stream));
+  c->launches += 5;
+  k_pp_tiled<T, TABLE, COUNT><<<c->num_sms * 8, 128, 0, c->stream>>>(
+      s.posm, s.cell_start, s.pp_items, order, s.pp_counters, g, sp, s.sr_table, s.acc, s.acc_sr,
+      s.pair_counts);
+  P3M_LAUNCH_CHECK(c);
+  k_pp_sparse<T, TABLE, COUNT><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(
+      s.posm, n, s.cell_start, g, sp, s.sr_table, s.acc, s.acc_sr, s.pair_counts);
+  P3M_LAUNCH_CHECK(c);
+  return 0;
+}
+
+template <typename T>
+int short_range(p3m_ctx* c) {
+  if (!c->prm.p3m) return 0;
+  if (!c->have_particles || !c->sorted) return fail(P3M_ESTATE, "p3m_short_range: particles not sorted");
+  if (c->n == 0) return 0;
+  phase_begin(c, PH_SHORT_RANGE);
+  int r;
+  const bool table = c->prm.use_sr_table != 0, count = c->count_pairs != 0;
+  if (table && !count) r = run_pp<T, true, false>(c);
+  else if (table && count) r = run_pp<T, true, true>(c);
+  else if (!table && !count) r = run_pp<T, false, false>(c);
+  else r = run_pp<T, false, true>(c);
+  phase_end(c, PH_SHORT_RANGE);
+  return r;
+}
+
+template int short_range<float>(p3m_ctx*);
+template int short_range<double>(p3m_ctx*);
+template int sr_table_upload<float>(p3m_ctx*);
+template int sr_table_upload<double>(p3m_ctx*);
+
+}  // namespace p3m

@@ -1,0 +1,469 @@
+"""GPU parity tests: the CUDA path (through the C ABI of include/p3m_b200.h) against the CPU oracle
+on the same seeded inputs.  Bars (BASELINE.json north_star):
+  * cell assignment and sort order: bit-exact;
+  * density, potential, accelerations: rel-L2 <= 1e-4 (fp32 path vs the fp32 oracle == reference),
+    <= 1e-6 (fp64 path vs the fp64 restatement);
+  * energy / momentum drift over 100 leapfrog steps matching the oracle's run.
+"""
+import numpy as np
+import pytest
+
+import refapi
+from common import (degenerate_mask, disk_case, morton3, plummer_case, project_out_degenerate, to_p3m,
+                    uniform_case)
+from particlesimulation_b200 import capi
+from refapi import Oracle, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL32 = 1e-4  # north_star: fp32 path
+TOL64 = 1e-6  # north_star: fp64 path
+
+_orc = {}
+
+
+def oracle(prec):
+    if prec not in _orc:
+        _orc[prec] = Oracle(prec)
+    return _orc[prec]
+
+
+def code_units(p, pos, vel, mass, prec="f32"):
+    return oracle(prec).to_code_units(p, pos, vel, mass)
+
+
+# --------------------------------------------------------------------------------------------- A0
+@pytest.mark.parametrize("p3m", [True, False])
+@pytest.mark.parametrize("n", [1, 37, 5000])
+def test_cells_and_sort_order_bit_exact(n, p3m):
+    p, pos, vel, mass = plummer_case(n)
+    pc, _, _ = code_units(p, pos, vel, mass)
+    with capi.Context(to_p3m(p, p3m=p3m)) as ctx:
+        ctx.set_particles(pos, vel, mass)
+        ctx.bin_sort()
+        mc, cc, order = ctx.cells()
+        gpos, _, _ = ctx.get_particles(capi.UNITS_CODE)
+        gdims = ctx.chaining_dims() if p3m else None
+    assert np.array_equal(gpos, pc), "code-unit positions must be bit-identical to the reference's"
+    # PM mesh cell: (int)pos, flat x + y*Nx + z*Nx*Ny  (source/pmMethod.cpp:250-252)
+    t = pc.astype(np.int32)  # truncation, positions are positive
+    assert np.array_equal(mc, t[:, 0] + t[:, 1] * p.nx + t[:, 2] * p.nx * p.ny)
+    if p3m:
+        dims, cell = oracle("f32").chaining_cells(p, pc)
+        assert np.array_equal(gdims, dims)
+        assert np.array_equal(cc, cell), "chaining-mesh cell ids must be bit-exact"
+        cx, cy, cz = cell % dims[0], (cell // dims[0]) % dims[1], cell // (dims[0] * dims[1])
+    else:
+        assert np.all(cc == -1)
+        cx, cy, cz = t[:, 0] >> 3, t[:, 1] >> 3, t[:, 2] >> 3
+    key = morton3(cx, cy, cz)
+    expect = np.lexsort((np.arange(n), key))  # stable: ties broken by particle id
+    assert np.array_equal(order, expect.astype(np.int32)), "sort order must be (z-order cell, id)"
+
+
+def test_sort_is_idempotent_and_deterministic():
+    p, pos, vel, mass = plummer_case(4096)
+    with capi.Context(to_p3m(p, p3m=True)) as ctx:
+        ctx.set_particles(pos, vel, mass)
+        ctx.bin_sort()
+        o1 = ctx.cells()[2]
+        ctx.bin_sort()
+        o2 = ctx.cells()[2]
+        g1 = ctx.get_particles(capi.UNITS_ORIGINAL, want=("pos",))[0]
+    assert np.array_equal(o1, o2)
+    assert np.allclose(g1, pos, rtol=2e-7, atol=0)  # H * (pos / H): one rounding pair
+
+
+# --------------------------------------------------------------------------------------------- A1
+@pytest.mark.parametrize("is_", [refapi.NGP, refapi.CIC, refapi.TSC])
+@pytest.mark.parametrize("case", ["plummer", "uniform", "disk"])
+def test_deposit_fp32(case, is_):
+    mk = dict(plummer=plummer_case, uniform=uniform_case, disk=disk_case)[case]
+    p, pos, vel, mass = mk(20000, is_=is_)
+    pc, _, mcode = code_units(p, pos, vel, mass)
+    rho_ref = oracle("f32").deposit(p, pc, mcode)
+    rho64 = oracle("f64").deposit(p, pc.astype(np.float64), mcode.astype(np.float64))
+    with capi.Context(to_p3m(p, p3m=(case != "uniform"))) as ctx:
+        ctx.set_particles(pos, vel, mass)
+        ctx.bin_sort()
+        ctx.deposit()
+        rho = ctx.density()
+    assert rel_l2(rho, rho_ref) < 1e-5
+    # and no further from the exact (fp64) assignment than the reference itself is
+    assert rel_l2(rho, rho64) < 2 * rel_l2(rho_ref, rho64) + 1e-7
+    assert abs(rho.sum(dtype=np.float64) - mcode.sum(dtype=np.float64)) < 1e-5 * mcode.sum(dtype=np.float64)
+
+
+def test_deposit_fp64():
+    p, pos, vel, mass = plummer_case(20000)
+    o = oracle("f64")
+    pc, _, mcode = o.to_code_units(p, pos, vel, mass)
+    rho_ref = o.deposit(p, pc, mcode)
+    with capi.Context(to_p3m(p, p3m=True, precision=capi.F64)) as ctx:
+        ctx.set_particles(pos, vel, mass)
+        ctx.bin_sort()
+        ctx.deposit()
+        rho = ctx.density(f64=True)
+    assert rel_l2(rho, rho_ref) < 1e-13
+
+
+def test_deposit_edge_particles():
+    """Particles on cell faces, at the origin corner (x-1 aliasing) and at the box face."""
+    p = refapi.make_params(8, (16, 16, 16), (8.0, 8.0, 8.0), H=1.0)
+    pos = np.array([[0.0, 3.5, 3.5], [1.0, 1.0, 1.0], [7.999, 7.999, 7.999], [4.0, 4.0, 4.0],
+                    [0.25, 0.25, 1.5], [3.0, 0.0, 2.0], [5.5, 5.5, 0.999], [2.0, 6.0, 6.0]], np.float32)
+    mass = np.linspace(1, 2, 8).astype(np.float32)
+    pc, _, mcode = code_units(p, pos, None, mass)
+    rho_ref = oracle("f32").deposit(p, pc, mcode)
+    for p3m in (False, True):
+        with capi.Context(to_p3m(p, p3m=p3m)) as ctx:
+            ctx.set_particles(pos, None, mass)
+            ctx.bin_sort()
+            ctx.deposit()
+            rho = ctx.density()
+        assert rel_l2(rho, rho_ref) < 1e-6
+
+
+# --------------------------------------------------------------------------------------------- A4
+@pytest.mark.parametrize("gfunc", [refapi.DISCRETE_LAPLACIAN, refapi.S1_OPTIMAL, refapi.S2_OPTIMAL,
+                                   refapi.POOR_MAN])
+@pytest.mark.parametrize("grid", [(16, 16, 16), (16, 8, 12)])
+def test_green_table(gfunc, grid):
+    p = refapi.make_params(1, grid, (60.0, 60.0, 60.0), gfunc=gfunc, zero_degenerate=True)
+    g64 = oracle("f64").green(p)
+    gsym = 0.5 * (g64 + np.roll(g64[::-1, ::-1, ::-1], 1, axis=(0, 1, 2)))  # G(k) + G(-k mod N)
+    with capi.Context(to_p3m(p, p3m=False, precision=capi.F64)) as ctx:
+        ctx.green_init()
+        g = ctx.get_green_table()
+    assert rel_l2(g, gsym) < 1e-10
+    # the fp32 reference table agrees away from the degenerate modes
+    p.greenZeroDegenerate = 0
+    g32 = oracle("f32").green(p).astype(np.float64)
+    g32sym = 0.5 * (g32 + np.roll(g32[::-1, ::-1, ::-1], 1, axis=(0, 1, 2)))
+    m = ~degenerate_mask(g32.shape) if gfunc in (refapi.S1_OPTIMAL, refapi.S2_OPTIMAL) else np.ones_like(g32, bool)
+    assert rel_l2(g[m], g32sym[m]) < 2e-5
+
+
+# ---------------------------------------------------------------------------------------- A2 + A3
+@pytest.mark.parametrize("grid", [(32, 32, 32), (32, 16, 8)])
+def test_poisson_with_reference_table(grid):
+    """FFT + multiply alone: density and Green table taken from the oracle."""
+    box = (60.0, 60.0 * grid[1] / grid[0], 60.0 * grid[2] / grid[0])
+    p, pos, vel, mass = plummer_case(20000, grid=grid, box=box, gfunc=refapi.DISCRETE_LAPLACIAN)
+    o = oracle("f32")
+    pc, _, mcode = o.to_code_units(p, pos, vel, mass)
+    rho = o.deposit(p, pc, mcode)
+    g = o.green(p)
+    phi_ref = o.poisson(p, rho, g)
+    phi64 = oracle("f64").poisson(p, rho.astype(np.float64), g.astype(np.float64))
+    with capi.Context(to_p3m(p, p3m=False)) as ctx:
+        ctx.set_green_table(g)
+        ctx.set_density(rho)
+        ctx.poisson()
+        phi = ctx.potential()
+    assert rel_l2(phi, phi_ref) < 5e-6
+    assert rel_l2(phi, phi64) < 5e-6
+
+
+def test_poisson_optimal_table_matches_c2c_real_part():
+    """R2C/C2R with the symmetrised table == the reference's C2C + .real()."""
+    p, pos, vel, mass = plummer_case(20000)
+    o = oracle("f32")
+    pc, _, mcode = o.to_code_units(p, pos, vel, mass)
+    rho = o.deposit(p, pc, mcode)
+    g = o.green(p)  # literal reference table, asymmetric, noise at the degenerate modes
+    phi_ref = o.poisson(p, rho, g)
+    with capi.Context(to_p3m(p, p3m=False)) as ctx:
+        ctx.set_green_table(g)
+        ctx.set_density(rho)
+        ctx.poisson()
+        phi = ctx.potential()
+    assert rel_l2(phi, phi_ref) < 5e-6
+
+
+# --------------------------------------------------------------------------------------------- A5
+@pytest.mark.parametrize("fds", [refapi.TWO_POINT, refapi.FOUR_POINT])
+def test_gradient_field(fds):
+    p, pos, vel, mass = plummer_case(5000, grid=(32, 16, 24), box=(60.0, 30.0, 45.0), fds=fds,
+                                     gfunc=refapi.DISCRETE_LAPLACIAN)
+    rng = np.random.default_rng(3)
+    phi = rng.standard_normal((p.nz, p.ny, p.nx)).astype(np.float32)
+    f_ref = oracle("f32").field(p, phi)
+    with capi.Context(to_p3m(p, p3m=False)) as ctx:
+        ctx.set_potential(phi)
+        ctx.gradient()
+        f = ctx.field()
+    assert rel_l2(f, f_ref) < 1e-6
+
+
+# --------------------------------------------------------------------------------------------- A6
+@pytest.mark.parametrize("is_,fds", [(refapi.TSC, refapi.TWO_POINT), (refapi.TSC, refapi.FOUR_POINT),
+                                     (refapi.CIC, refapi.TWO_POINT), (refapi.NGP, refapi.TWO_POINT)])
+@pytest.mark.parametrize("case", ["plummer", "disk"])
+def test_gather(case, is_, fds):
+    mk = dict(plummer=plummer_case, disk=disk_case)[case]
+    p, pos, vel, mass = mk(20000, is_=is_, fds=fds, gfunc=refapi.DISCRETE_LAPLACIAN)
+    o = oracle("f32")
+    pc, _, mcode = o.to_code_units(p, pos, vel, mass)
+    rng = np.random.default_rng(5)
+    phi = rng.standard_normal((p.nz, p.ny, p.nx)).astype(np.float32)
+    acc_ref = o.gather(p, pc, o.field(p, phi))
+    for p3m in (False, True):
+        with capi.Context(to_p3m(p, p3m=p3m)) as ctx:
+            ctx.set_particles(pos, vel, mass)
+            ctx.bin_sort()
+            ctx.set_potential(phi)
+            ctx.gather()
+            acc = ctx.get_particles(capi.UNITS_CODE, want=("acc",))[2]
+        assert rel_l2(acc, acc_ref) < 5e-6, f"p3m={p3m}"
+
+
+# ----------------------------------------------------------------------------------- A7, A8, A9
+@pytest.mark.parametrize("use_table,cloud", [(True, refapi.S1), (True, refapi.S2), (False, refapi.S1),
+                                             (False, refapi.S2)])
+def test_short_range_forces(use_table, cloud):
+    p, pos, vel, mass = plummer_case(6000, use_table=use_table, cloud=cloud,
+                                     gfunc=refapi.S1_OPTIMAL if cloud == refapi.S1 else refapi.S2_OPTIMAL)
+    o = oracle("f32")
+    pc, _, mcode = o.to_code_units(p, pos, vel, mass)
+    sr_ref = o.sr_forces(p, pc, mcode) / mcode[:, None]
+    with capi.Context(to_p3m(p, p3m=True)) as ctx:
+        ctx.set_particles(pos, vel, mass)
+        if use_table:
+            assert rel_l2(ctx.sr_table(), o.sr_table(p)) < 1e-7
+        ctx.bin_sort()
+        ctx.short_range()
+        _, sr = ctx.acc_parts()
+    assert rel_l2(sr, sr_ref) < 2e-5
+    # Newton's third law: total short-range force vanishes
+    f = sr * mcode[:, None].astype(np.float64)
+    assert np.abs(f.sum(axis=0)).max() < 1e-5 * np.abs(f).sum()
+
+
+def test_short_range_fp64():
+    p, pos, vel, mass = plummer_case(6000)
+    o = oracle("f64")
+    pc, _, mcode = o.to_code_units(p, pos, vel, mass)
+    sr_ref = o.sr_forces(p, pc, mcode) / mcode[:, None]
+    with capi.Context(to_p3m(p, p3m=True, precision=capi.F64)) as ctx:
+        ctx.set_particles(pos, vel, mass)
+        ctx.bin_sort()
+        ctx.short_range()
+        _, sr = ctx.acc_parts()
+    assert rel_l2(sr, sr_ref) < 1e-9
+
+
+def test_short_range_dense_and_sparse_paths_agree_with_direct_sum():
+    """A tight clump (dense-cell tiled kernel) inside a sparse halo (per-target kernel)."""
+    rng = np.random.default_rng(11)
+    n1, n2 = 3000, 3000
+    clump = 30.0 + 0.8 * rng.standard_normal((n1, 3))
+    halo = 30.0 + 12.0 * (rng.random((n2, 3)) - 0.5)
+    pos = np.concatenate([clump, halo]).astype(np.float32)
+    mass = np.full(n1 + n2, 1.0 / (n1 + n2), np.float32)
+    p = refapi.make_params(n1 + n2, (32, 32, 32), (60.0, 60.0, 60.0))
+    o = oracle("f64")
+    pc, _, mcode = o.to_code_units(p, pos, None, mass)
+    sr_ref = o.sr_forces(p, pc, mcode) / mcode[:, None]
+    with capi.Context(to_p3m(p, p3m=True)) as ctx:
+        ctx.set_particles(pos, None, mass)
+        ctx.bin_sort()
+        ctx.short_range()
+        _, sr = ctx.acc_parts()
+        checked, inside = ctx.pair_counts()
+    assert rel_l2(sr, sr_ref) < 2e-5
+    from scipy.spatial import cKDTree
+    tree = cKDTree(pc)
+    re = float(p.cutoffRadius) / float(p.H)
+    expect = int(tree.count_neighbors(tree, re)) - (n1 + n2)  # ordered pairs i != j within the cutoff
+    assert abs(inside - expect) <= 1e-3 * expect
+    assert checked >= inside
+
+
+# ------------------------------------------------------------------------------- whole force step
+@pytest.mark.parametrize("case,p3m", [("plummer", False), ("plummer", True), ("disk", False), ("disk", True)])
+def test_force_fp32_vs_oracle(case, p3m):
+    mk = dict(plummer=plummer_case, disk=disk_case)[case]
+    p, pos, vel, mass = mk(20000)
+    o = oracle("f32")
+    pc, _, mcode = o.to_code_units(p, pos, vel, mass)
+    g = o.green(p)
+    rho_ref, phi_ref, acc_ref = o.force(p, p3m, g, pc, mcode)
+    with capi.Context(to_p3m(p, p3m=p3m, zero_degenerate=True)) as ctx:
+        ctx.set_particles(pos, vel, mass)
+        ctx.force()
+        rho, phi = ctx.density(), ctx.potential()
+        acc = ctx.get_particles(capi.UNITS_CODE, want=("acc",))[2]
+    assert rel_l2(rho, rho_ref) < TOL32
+    # potential: compare with the degenerate modes (reference = rounding noise there) projected out
+    assert rel_l2(project_out_degenerate(phi), project_out_degenerate(phi_ref)) < TOL32
+    assert rel_l2(acc, acc_ref) < TOL32
+
+
+@pytest.mark.parametrize("p3m", [False, True])
+def test_force_fp64_vs_oracle(p3m):
+    p, pos, vel, mass = plummer_case(20000, zero_degenerate=True)
+    o = oracle("f64")
+    pc, _, mcode = o.to_code_units(p, pos, vel, mass)
+    g = o.green(p)
+    rho_ref, phi_ref, acc_ref = o.force(p, p3m, g, pc, mcode)
+    with capi.Context(to_p3m(p, p3m=p3m, precision=capi.F64)) as ctx:
+        ctx.set_particles(pos, vel, mass)
+        ctx.force()
+        rho, phi = ctx.density(f64=True), ctx.potential(f64=True)
+        acc = ctx.get_particles(capi.UNITS_CODE, f64=True, want=("acc",))[2]
+    assert rel_l2(rho, rho_ref) < TOL64
+    assert rel_l2(phi, phi_ref) < TOL64
+    assert rel_l2(acc, acc_ref) < TOL64
+
+
+@pytest.mark.skipif(not refapi.have_ref(), reason="oracle/_ref not built")
+def test_force_fp32_vs_compiled_reference():
+    """Straight against the UNMODIFIED reference (oracle/_ref), P3M, reference demo parameters."""
+    p, pos, vel, mass = plummer_case(20000)
+    r = refapi.Ref().p3m_force(p, pos, vel, mass)
+    with capi.Context(to_p3m(p, p3m=True, zero_degenerate=True)) as ctx:
+        ctx.set_particles(pos, vel, mass)
+        ctx.force()
+        acc = ctx.get_particles(capi.UNITS_CODE, want=("acc",))[2]
+        mc, cc, order = ctx.cells()
+    assert np.array_equal(cc, r["cell"])
+    assert rel_l2(acc, r["acc"]) < TOL32
+
+
+def test_force_is_deterministic_in_short_range_and_sort():
+    p, pos, vel, mass = plummer_case(20000)
+    out = []
+    for _ in range(2):
+        with capi.Context(to_p3m(p, p3m=True)) as ctx:
+            ctx.set_particles(pos, vel, mass)
+            ctx.force()
+            out.append((ctx.cells()[2], ctx.acc_parts()[1]))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1]), "short-range sums are order-fixed, hence bit-reproducible"
+
+
+# ------------------------------------------------------------------------------------ A10, A11, N1
+@pytest.mark.parametrize("case,p3m", [("plummer", True), ("disk", False)])
+def test_run_100_steps_energy_momentum_drift(case, p3m):
+    mk = dict(plummer=plummer_case, disk=disk_case)[case]
+    n, steps = 4000, 100
+    p, pos, vel, mass = mk(n, gfunc=refapi.DISCRETE_LAPLACIAN if not p3m else refapi.S1_OPTIMAL)
+    diag_ref, pos_ref, vel_ref, _ = oracle("f32").run(p, p3m, pos, vel, mass, steps)
+    assert diag_ref.shape[0] == steps + 1 and not diag_ref[:, 11].any(), "oracle run must not escape"
+    rows = []
+    with capi.Context(to_p3m(p, p3m=p3m, zero_degenerate=True)) as ctx:
+        # head of run(): source/pmMethod.cpp:72-77 / source/p3mMethod.cpp:73-91
+        ctx.set_particles(pos, vel, mass)
+        ctx.green_init()
+        ctx.force()
+        ctx.kick(0.5)
+        for t in range(steps + 1):
+            ctx.drift()
+            rows.append(ctx.diagnostics())
+            assert not ctx.escaped()
+            ctx.force()
+            ctx.kick(1.0)
+        gpos, gvel, _ = ctx.get_particles(capi.UNITS_CODE)
+    d = np.array(rows)
+    e_ref = diag_ref[:, 0] + diag_ref[:, 1]
+    e = d[:, 0] + d[:, 1]
+    scale = np.abs(diag_ref[:, 1]).max()
+    # energy trajectory: same drift (difference small against the kinetic energy scale)
+    assert np.abs(e - e_ref).max() < 2e-3 * scale, (np.abs(e - e_ref).max(), scale)
+    assert np.abs((e[-1] - e[0]) - (e_ref[-1] - e_ref[0])) < 2e-3 * scale
+    # momentum and angular momentum trajectories
+    pscale = np.abs(mass.astype(np.float64)[:, None] * vel).sum()
+    assert np.abs(d[:, 2:5] - diag_ref[:, 2:5]).max() < 2e-3 * pscale
+    lscale = np.abs(diag_ref[:, 5:8]).max() + 1e-30
+    assert np.abs(d[:, 5:8] - diag_ref[:, 5:8]).max() < 5e-3 * lscale
+    # trajectories stay together (chaotic divergence is still small after 100 steps)
+    assert rel_l2(gpos, pos_ref) < 1e-3
+
+
+def test_step_matches_manual_sequence_and_stops_on_escape():
+    p, pos, vel, mass = plummer_case(2000)
+    with capi.Context(to_p3m(p, p3m=True)) as a, capi.Context(to_p3m(p, p3m=True)) as b:
+        for ctx in (a, b):
+            ctx.set_particles(pos, vel, mass)
+            ctx.force()
+            ctx.kick(0.5)
+        assert a.step(5) == 5
+        for _ in range(5):
+            b.drift(); b.force(); b.kick(1.0)
+        pa = a.get_particles(capi.UNITS_CODE)
+        pb = b.get_particles(capi.UNITS_CODE)
+        assert np.array_equal(pa[0], pb[0]) and np.array_equal(pa[1], pb[1])
+    # a particle that leaves the box freezes the state (source/pmMethod.cpp:108-111)
+    vel2 = vel.copy()
+    vel2[0] = [40.0, 0.0, 0.0]
+    with capi.Context(to_p3m(p, p3m=True)) as ctx:
+        ctx.set_particles(pos, vel2, mass)
+        ctx.force()
+        ctx.kick(0.5)
+        done = ctx.step(10)
+        assert done < 10
+        assert ctx.escaped()
+
+
+# ------------------------------------------------------------------------------------------ errors
+def test_error_behaviour():
+    p = capi.default_params()
+    p.nx = p.ny = p.nz = 16
+    p.box[:] = [8.0, 8.0, 8.0]
+    p.assignment = 7
+    with pytest.raises(capi.P3MError) as e:
+        capi.Context(p)
+    assert e.value.code == -1 and "interpolation scheme" in str(e.value)
+    p.assignment = capi.TSC
+    with capi.Context(p) as ctx:
+        with pytest.raises(capi.P3MError) as e:
+            ctx.deposit()
+        assert e.value.code == -4
+        ctx.set_particles(np.zeros((0, 3), np.float32), None, np.zeros(0, np.float32))
+        ctx.force()  # empty input is legal
+        assert ctx.density().sum() == 0
+
+
+# --------------------------------------------------------- full-size, size-independent properties
+def test_config2_full_size_properties():
+    """BASELINE config 2 (P3M Plummer, 2^20 particles, 128^3, TSC): properties that need no oracle."""
+    n = 1 << 20
+    p, pos, vel, mass = plummer_case(n, grid=(128, 128, 128), softening=0.5)
+    with capi.Context(to_p3m(p, p3m=True)) as ctx:
+        ctx.set_particles(pos, vel, mass)
+        ctx.force()
+        rho = ctx.density(f64=True)
+        mc, cc, order = ctx.cells()
+        _, sr = ctx.acc_parts()
+        gpos, _, acc = ctx.get_particles(capi.UNITS_CODE)
+        pc, _, mcode = code_units(p, pos, vel, mass)
+    # mass conservation of the assignment
+    assert abs(rho.sum() - mcode.sum(dtype=np.float64)) < 1e-5 * mcode.sum(dtype=np.float64)
+    # order is a permutation, cell-sorted
+    assert np.array_equal(np.sort(order), np.arange(n))
+    dims, cell = oracle("f32").chaining_cells(p, pc)
+    assert np.array_equal(cc, cell)
+    key = morton3(cell % dims[0], (cell // dims[0]) % dims[1], cell // (dims[0] * dims[1]))
+    assert np.all(np.diff(key[order].astype(np.int64)) >= 0)
+    # Newton's third law for the short-range part; finite accelerations
+    f = sr * mcode[:, None].astype(np.float64)
+    assert np.abs(f.sum(axis=0)).max() < 1e-4 * np.abs(f).sum()
+    assert np.isfinite(acc).all()
+    # a sample of particles against the direct O(N) evaluation of the same short-range sum (fp64)
+    o = oracle("f64")
+    tab = o.sr_table(p)
+    re2 = (float(p.cutoffRadius) / float(p.H)) ** 2
+    d2t = re2 / 499.0
+    rng = np.random.default_rng(0)
+    pc64 = pc.astype(np.float64); m64 = mcode.astype(np.float64)
+    for i in rng.choice(n, 8, replace=False):
+        d = pc64[i][None, :] - pc64
+        r2 = (d * d).sum(1)
+        sel = (r2 < re2)
+        xi = r2[sel] / d2t
+        t = np.minimum(xi.astype(np.int64), 498)
+        fr = xi - t
+        F = tab[t] + fr * (tab[t + 1] - tab[t])
+        a = (m64[sel] * F)[:, None] * d[sel]
+        assert np.allclose(sr[i], a.sum(0), rtol=2e-3, atol=1e-3 * np.abs(a).sum(0).max() + 1e-30)
