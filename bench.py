@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of BASELINE.json: P3M particle-steps/s.
+
+  python bench.py --gpus N --steps K --warmup W            our arm   (C ABI -> sm_100a kernels)
+  python bench.py --impl reference --steps K --warmup W     the reference's own CPU path, same host
+
+One "step" = one pass of the hot path: drift -> bin/sort -> deposit -> Poisson -> gather -> short range
+-> kick (the body of the reference's run loop, source/p3mMethod.cpp:101-153).  At N = 1 the workload is
+BASELINE.json configs[1]: P3M Plummer sphere, 2^20 particles, 128^3 mesh, TSC, S1-optimal influence
+function, a = 3H, re = 0.7a, eps = 0.5, tabulated short-range force (source/demos.cpp:1416-1447).
+
+`value`   particle-steps/s with the particles resident in HBM (CUDA events on the context's stream).
+`e2e`     the same step through the C ABI with HOST buffers: p3m_set_particles (H2D from pinned
+          memory) + p3m_step(1) + p3m_get_particles (D2H) inside the timed region -- what the
+          reference's own CUDA build does every P3M step (source/p3mMethod.cpp:143-151).
+`roofline` the dominant kernel (short-range PP, FP32 pipe) + per-kernel HBM figures in `roofline_kernels`.
+`cpu_baseline` the UNMODIFIED reference compiled in oracle/_ref, timed on this host on a bounded sample.
+Nothing under oracle/ is used by the GPU arm's timed path.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_C2 = 1 << 20
+GRID_C2 = (128, 128, 128)
+BOX_C2 = (60.0, 60.0, 60.0)
+
+
+# ---------------------------------------------------------------------------------------- cudart
+class Cuda:
+    def __init__(self):
+        self.rt = C.CDLL("libcudart.so.12")
+        self.rt.cudaEventElapsedTime.argtypes = [C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
+        self.rt.cudaEventRecord.argtypes = [C.c_void_p, C.c_void_p]
+        self.rt.cudaEventSynchronize.argtypes = [C.c_void_p]
+        self.rt.cudaMemsetAsync.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]
+        self.rt.cudaHostAlloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.c_uint]
+        self.rt.cudaMalloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+
+    def check(self, rc, what=""):
+        if rc != 0:
+            raise RuntimeError(f"CUDA error {rc} {what}")
+
+    def event(self):
+        e = C.c_void_p()
+        self.check(self.rt.cudaEventCreate(C.byref(e)), "cudaEventCreate")
+        return e
+
+    def record(self, e, stream):
+        self.check(self.rt.cudaEventRecord(e, stream), "cudaEventRecord")
+
+    def elapsed_ms(self, a, b):
+        self.check(self.rt.cudaEventSynchronize(b), "cudaEventSynchronize")
+        ms = C.c_float(0)
+        self.check(self.rt.cudaEventElapsedTime(C.byref(ms), a, b), "cudaEventElapsedTime")
+        return float(ms.value)
+
+    def pinned(self, shape, dtype=np.float32):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self.check(self.rt.cudaHostAlloc(C.byref(p), max(n, 16), 0), "cudaHostAlloc")
+        buf = (C.c_byte * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def malloc(self, nbytes):
+        p = C.c_void_p()
+        self.check(self.rt.cudaMalloc(C.byref(p), nbytes), "cudaMalloc")
+        return p
+
+    def set_device(self, d):
+        self.check(self.rt.cudaSetDevice(d), "cudaSetDevice")
+
+    def sync(self):
+        self.check(self.rt.cudaDeviceSynchronize(), "cudaDeviceSynchronize")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# -------------------------------------------------------------------------------------- workloads
+def c2_params(capi, timing=False):
+    """BASELINE.json configs[1] with the reference demo's parameters (source/demos.cpp:1416-1447)."""
+    f32 = np.float32
+    p = capi.default_params()
+    p.nx, p.ny, p.nz = GRID_C2
+    p.box[:] = BOX_C2
+    p.H = f32(f32(BOX_C2[0]) / f32(GRID_C2[0] // 2))
+    p.DT, p.G = 1.0, 4.5e-3
+    p.assignment, p.fd_scheme, p.greens_function = capi.TSC, capi.TWO_POINT, capi.S1_OPTIMAL
+    p.particle_diameter = f32(f32(3) * f32(p.H))
+    p.p3m = 1
+    p.cutoff_radius = f32(f32(0.7) * f32(p.particle_diameter))
+    p.softening = 0.5
+    p.cloud_shape, p.use_sr_table = capi.S1, 1
+    p.precision = capi.F32
+    p.unit_roundtrip = 1
+    p.green_zero_degenerate = 1
+    p.timing = int(timing)
+    return p
+
+
+def c2_particles(n):
+    from particlesimulation_b200 import ics
+    return ics.plummer(n, center=(30.0, 30.0, 30.0), a=2.0, r_max=15.0, M=1.0, G=4.5e-3, seed=42)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+# ------------------------------------------------------------------------------------ reference arm
+def reference_sample_params(n):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refapi
+    return refapi, refapi.make_params(n, GRID_C2, BOX_C2, softening=0.5)
+
+
+def run_reference(args, as_baseline=False):
+    """The reference's own CPU implementation of the path (oracle/_ref = its unmodified sources),
+    on a bounded sample of the workload: same mesh, same physics, fewer particles."""
+    n = int(os.environ.get("P3M_BENCH_CPU_N", 1 << 15))
+    steps = max(1, args.steps if not as_baseline else 2)
+    warm = 0
+    refapi, p = reference_sample_params(n)
+    pos, vel, mass = c2_particles(n)
+    if refapi.have_ref():
+        ref = refapi.Ref()
+        cores = ref.hardware_threads()
+        t0 = time.time()
+        ms, green_ms = ref.time_steps(p, pos, vel, mass, steps, True)
+        wall = time.time() - t0
+        kind = "reference"
+        total_ms = ms["total"]
+        breakdown = {k: round(v / steps, 3) for k, v in ms.items() if k != "total"}
+        note = (f"unmodified reference sources (oracle/_ref, g++ -O3, kissfft; PM loops serial: libstdc++ PSTL "
+                f"without TBB; short-range loop on {cores} std::threads)")
+    else:
+        o = refapi.Oracle("f32")
+        cores = 1
+        t0 = time.time()
+        o.run(p, True, pos, vel, mass, steps - 1, diagnostics=False)
+        total_ms = (time.time() - t0) * 1e3
+        wall = total_ms / 1e3
+        green_ms = float("nan")
+        kind = "port"
+        breakdown = {}
+        note = "oracle/p3m_oracle.c (scalar C restatement, includes the influence-function set-up)"
+    value = n * steps / (total_ms / 1e3)
+    sample = (f"P3M Plummer N={n} (of 2^20) on the full 128^3 mesh, {steps} steps after one untimed force "
+              f"evaluation; influence-function init {green_ms / 1e3:.1f} s excluded; {note}. Short-range cost grows "
+              f"~N^2 in the Plummer core, so the full-size CPU step is far slower than this sample suggests.")
+    base = {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": kind, "sample": sample,
+            "ms_per_step": total_ms / steps, "ms_per_step_by_phase": breakdown, "wall_s": round(wall, 1)}
+    if as_baseline:
+        return base
+    line = {"impl": "reference", "metric": "P3M particle-steps/s", "value": value, "unit": "particle-steps/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": total_ms / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2 P3M Plummer 128^3 TSC (bounded CPU sample)", "particles": n,
+                       "mesh": list(GRID_C2)},
+            "cpu_baseline": base,
+            "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return line
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    from particlesimulation_b200 import capi
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1 or args.gpus > 1:
+        return run_ours_multi(args, rank, world, local)
+
+    cu = Cuda()
+    cu.set_device(0)
+    n = int(os.environ.get("P3M_BENCH_N", N_C2))
+    pos, vel, mass = c2_particles(n)
+    hbm_peak, peak_src, sm_max = load_peaks()
+
+    ctx = capi.Context(c2_params(capi))
+    stream = ctx.stream
+    ctx.set_particles(pos, vel, mass)
+    ctx.green_init()
+    ctx.force()
+    ctx.kick(0.5)  # setHalfStepVelocities
+    flush_bytes = 256 << 20
+    flush = cu.malloc(flush_bytes)
+    for _ in range(args.warmup):
+        ctx.step(1)
+    ev = [(cu.event(), cu.event()) for _ in range(args.steps)]
+    launches0 = ctx.launches
+    clocks = ClockSampler(0)
+    clocks.start()
+    cu.sync()
+    t_wall0 = time.time()
+    for a, b in ev:
+        cu.check(cu.rt.cudaMemsetAsync(flush, 0, flush_bytes, stream), "flush")  # evict L2 (126 MB)
+        cu.record(a, stream)
+        ctx.step(1)
+        cu.record(b, stream)
+    cu.sync()
+    t_wall = time.time() - t_wall0
+    clk = clocks.stop()
+    launches = ctx.launches - launches0
+    ms = [cu.elapsed_ms(a, b) for a, b in ev]
+    total_ms = float(np.sum(ms))
+    value = n * args.steps / (total_ms / 1e3)
+
+    # ---- end to end through the C ABI with host buffers (pinned), one step per call triple
+    hp, hv, hm = cu.pinned((n, 3)), cu.pinned((n, 3)), cu.pinned((n,))
+    op, ov = cu.pinned((n, 3)), cu.pinned((n, 3))
+    cpos, cvel, _ = ctx.get_particles(capi.UNITS_ORIGINAL)
+    hp[:], hv[:], hm[:] = cpos, cvel, mass
+    e2e_steps = max(2, min(args.steps, 5))
+    lib = capi.lib()
+    t0 = None
+    for it in range(e2e_steps + 1):
+        if it == 1:
+            cu.sync()
+            t0 = time.time()
+        ctx.set_particles(hp, hv, hm)          # H2D: pos, vel, mass (28 B / particle)
+        ctx.step(1)                             # drift -> force -> kick (self-contained: needs x, v, m only)
+        rc = lib.p3m_get_particles(ctx._h, op.ctypes.data_as(C.c_void_p), ov.ctypes.data_as(C.c_void_p), None,
+                                   capi.UNITS_ORIGINAL)  # D2H: pos, vel (24 B / particle)
+        assert rc == 0
+        hp[:], hv[:] = op, ov
+    e2e_s = (time.time() - t0) / e2e_steps
+    e2e_value = n / e2e_s
+
+    # ---- per-phase breakdown and roofline figures from a timing context (CUDA events per phase)
+    tctx = capi.Context(c2_params(capi, timing=True))
+    tctx.set_particles(pos, vel, mass)
+    tctx.green_init()
+    tctx.force()
+    tctx.kick(0.5)
+    tctx.step(2)
+    tctx.phase_ms(reset=True)
+    psteps = 3
+    tctx.step(psteps)
+    phases = {k: v / psteps for k, v in tctx.phase_ms().items()}
+    checked, inside = tctx.pair_counts()
+    tctx.close()
+    M = GRID_C2[0] * GRID_C2[1] * GRID_C2[2]
+    # flops = 9 * P_checked + 14 * P_in
+    pp_flops = 9.0 * checked + 14.0 * inside
+    pp_ms = phases["shortRangeForcesCalc"]
+    sm_count = 148
+    fp32_peak = sm_count * 128 * 2 * sm_max * 1e6 / 1e12  # TFLOP/s at clocks.max.sm, FMA = 2 flop
+    pp_tflops = pp_flops / (pp_ms / 1e3) / 1e12 if pp_ms > 0 else 0.0
+
+    def hbm(bytes_, ms_):
+        gbs = bytes_ / (ms_ / 1e3) / 1e9 if ms_ > 0 else 0.0
+        return {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                "algorithmic_bytes": bytes_, "ms": ms_}
+
+    kernels = {
+        "binSort": hbm(76.0 * n, phases["binSort"]),
+        "spreadMass": hbm(16.0 * n + 8.0 * M, phases["spreadMass"]),
+        "poisson(fwdFFT+multiply+invFFT)": hbm(18.0 * M, phases["forwardFFT"] + phases["fourierPotential"] + phases["inverseFFT"]),
+        "updateAccelerations(fused gradient+gather)": hbm(4.0 * M + 28.0 * n, phases["updateAccelerations"]),
+        "integrate": hbm(2 * 48.0 * n, phases["integrate"]),
+    }
+    roofline = {"kernel": "k_pp_tiled (short-range PP, dense chaining cells)", "bound": "fp32",
+                "achieved": pp_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": pp_tflops / fp32_peak if fp32_peak else None, "traffic": None,
+                "peak_source": f"148 SMs x 128 FP32 lanes x 2 flop x clocks.max.sm {sm_max:.0f} MHz (no tensor cores on "
+                               f"this path; HBM peak for the other kernels: {peak_src})",
+                "flops_per_launch": pp_flops, "pairs_checked": checked, "pairs_in_range": inside,
+                "ms": pp_ms}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            cpu = run_reference(args, as_baseline=True)
+        except Exception as e:  # the GPU numbers stand on their own
+            cpu = {"value": None, "unit": "particle-steps/s", "cores": 0, "kind": "reference",
+                   "sample": f"failed: {e}"}
+
+    line = {
+        "metric": "P3M particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: P3M Plummer sphere, 2^20 particles, 128^3 mesh, TSC, S1-optimal Green, "
+                               "chaining-mesh PP (re=0.7a, a=3H, eps=0.5, table)", "particles": n,
+                   "mesh": list(GRID_C2), "l2": "256 MiB memset between timed steps (outside the events)",
+                   "parallelism": "1 GPU"},
+        "clocks": clk, "gpu_launches": launches,
+        "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": 28 * n,
+                "d2h_bytes_per_step": 24 * n, "ms_per_step": e2e_s * 1e3},
+        "roofline": roofline, "roofline_kernels": kernels,
+        "ms_per_step_by_phase": phases, "ms_per_step_each": ms, "wall_s_timed_region": t_wall,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    ctx.close()
+    return line
+
+
+def run_ours_multi(args, rank, world, local):
+    raise SystemExit("bench.py: the multi-GPU z-slab path is not built yet (DESIGN.md section 7); run with --gpus 1")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", 0)) != 0:
+            return
+        run_reference(args)
+        return
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -88,8 +88,10 @@ def test_deposit_fp32(case, is_):
         ctx.bin_sort()
         ctx.deposit()
         rho = ctx.density()
-    assert rel_l2(rho, rho_ref) < 1e-5
-    # and no further from the exact (fp64) assignment than the reference itself is
+    # the reference adds particle by particle in fp32 (biased rounding in dense cells: up to ~1e-4 for
+    # NGP with equal masses); the bar is the north-star tolerance against it ...
+    assert rel_l2(rho, rho_ref) < TOL32
+    # ... and no further from the exact (fp64) assignment than the reference itself is
     assert rel_l2(rho, rho64) < 2 * rel_l2(rho_ref, rho64) + 1e-7
     assert abs(rho.sum(dtype=np.float64) - mcode.sum(dtype=np.float64)) < 1e-5 * mcode.sum(dtype=np.float64)
 
