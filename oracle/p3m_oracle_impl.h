@@ -164,6 +164,14 @@ static inline R FN(tsc_w)(R x, int t) {
   return ((R)0.5 - x) * ((R)0.5 - x);
 }
 
+/* Out-of-array indices are undefined behaviour in the reference (vector::operator[] past the end,
+ * only reachable for particles outside [1, N-2] cells); the oracle skips them instead of crashing. */
+#define DEP(idx, v)                                        \
+  do {                                                     \
+    size_t i__ = (idx);                                    \
+    if (i__ < M) density[i__] += (v);                      \
+  } while (0)
+
 void FN(orc_deposit)(const OrcParams* p, const R* pos, const R* mass, R* density) {
   const size_t M = (size_t)p->nx * p->ny * p->nz;
   memset(density, 0, M * sizeof(R)); /* grid.cpp:34-36 clearDensity */
@@ -171,19 +179,19 @@ void FN(orc_deposit)(const OrcParams* p, const R* pos, const R* mass, R* density
     R px = pos[3 * i], py = pos[3 * i + 1], pz = pos[3 * i + 2], d = mass[i];
     if (p->is == 0) { /* NGP :204-213 */
       int x = (int)ROUND(px), y = (int)ROUND(py), z = (int)ROUND(pz);
-      density[FN(flat)(p, x, y, z)] += d;
+      DEP(FN(flat)(p, x, y, z), d);
     } else if (p->is == 1) { /* CIC :216-244, no periodic wrap (grid.cpp:28-32) */
       int x = (int)px, y = (int)py, z = (int)pz;
       R dx = px - x, dy = py - y, dz = pz - z;
       R tx = 1 - dx, ty = 1 - dy, tz = 1 - dz;
-      density[FN(flat)(p, x, y, z)] += d * tx * ty * tz;
-      density[FN(flat)(p, x + 1, y, z)] += d * dx * ty * tz;
-      density[FN(flat)(p, x, y + 1, z)] += d * tx * dy * tz;
-      density[FN(flat)(p, x, y, z + 1)] += d * tx * ty * dz;
-      density[FN(flat)(p, x + 1, y + 1, z)] += d * dx * dy * tz;
-      density[FN(flat)(p, x + 1, y, z + 1)] += d * dx * ty * dz;
-      density[FN(flat)(p, x, y + 1, z + 1)] += d * tx * dy * dz;
-      density[FN(flat)(p, x + 1, y + 1, z + 1)] += d * dx * dy * dz;
+      DEP(FN(flat)(p, x, y, z), d * tx * ty * tz);
+      DEP(FN(flat)(p, x + 1, y, z), d * dx * ty * tz);
+      DEP(FN(flat)(p, x, y + 1, z), d * tx * dy * tz);
+      DEP(FN(flat)(p, x, y, z + 1), d * tx * ty * dz);
+      DEP(FN(flat)(p, x + 1, y + 1, z), d * dx * dy * tz);
+      DEP(FN(flat)(p, x + 1, y, z + 1), d * dx * ty * dz);
+      DEP(FN(flat)(p, x, y + 1, z + 1), d * tx * dy * dz);
+      DEP(FN(flat)(p, x + 1, y + 1, z + 1), d * dx * dy * dz);
     } else { /* TSC :247-272, truncation base */
       int x = (int)px, y = (int)py, z = (int)pz;
       R dx = px - x, dy = py - y, dz = pz - z;
@@ -193,7 +201,7 @@ void FN(orc_deposit)(const OrcParams* p, const R* pos, const R* mass, R* density
           R T2 = T1 * FN(tsc_w)(dy, t2);
           for (int t3 = -1; t3 <= 1; ++t3) {
             R T3 = T2 * FN(tsc_w)(dz, t3);
-            density[FN(flat)(p, x + t1, y + t2, z + t3)] += T3;
+            DEP(FN(flat)(p, x + t1, y + t2, z + t3), T3);
           }
         }
       }
@@ -362,7 +370,8 @@ static R FN(ext_potential)(const OrcParams* p, FN(V3) pos) {
 
 static inline FN(V3) FN(fld)(const OrcParams* p, const R* f, int x, int y, int z) {
   size_t i = FN(flat)(p, x, y, z); /* grid.cpp:46-48 getField: NOT wrapped */
-  FN(V3) v = {f[3 * i], f[3 * i + 1], f[3 * i + 2]};
+  FN(V3) v = {0, 0, 0};
+  if (i < (size_t)p->nx * p->ny * p->nz) v.x = f[3 * i], v.y = f[3 * i + 1], v.z = f[3 * i + 2];
   return v;
 }
 
@@ -762,6 +771,7 @@ int FN(orc_run)(const OrcParams* p, int p3m, const float* pos0, const float* vel
 }
 
 #undef ACCW
+#undef DEP
 #undef FN
 #undef FN1
 #undef FN2

@@ -46,7 +46,8 @@ def disk_case(n, grid=(32, 32, 16), box=(60.0, 60.0, 30.0), seed=42, **kw):
     return p, pos, vel, mass
 
 
-def uniform_case(n, grid=(32, 32, 32), box=(60.0, 60.0, 60.0), seed=7, margin=0.02, **kw):
+def uniform_case(n, grid=(32, 32, 32), box=(60.0, 60.0, 60.0), seed=7, margin=0.08, **kw):
+    # margin keeps every TSC stencil inside the mesh arrays (base cell >= 1), the reference's domain
     lo = [margin * b for b in box]
     hi = [(1 - margin) * b for b in box]
     pos, vel, mass = ics.uniform_cube(n, lo, hi, total_mass=1.0, seed=seed)
