@@ -146,6 +146,16 @@ int p3m_step(p3m_ctx* ctx, int steps, int* steps_done);
 /* PMMethod::escapedComputationalBox on the current positions. */
 int p3m_escaped(p3m_ctx* ctx, int* escaped);
 
+/* Slow path for an arbitrary host `externalField` std::function (source/pmMethod.cpp:384-390): the
+ * caller evaluates it on downloaded positions and adds the result (3N values, original particle
+ * order; units as given) to the accelerations of the last force evaluation. */
+int p3m_add_acceleration(p3m_ctx* ctx, const float* acc_xyz, int units);
+
+/* FFTAdapter<float>::fft / ifft (include/FFTAdapter.h:11-14) on host buffers of nz*ny*nx interleaved
+ * complex floats, x fastest: forward unnormalised, inverse divided by the length -- the contract of
+ * test/fftAdaptersTest.cpp:6-22.  Needs no context; backs the CuFFTAdapter host class. */
+int p3m_fft3d_c2c(int nz, int ny, int nx, const float* in, float* out, int inverse);
+
 /* N1: SimInfo diagnostics on the device (source/simInfo.cpp:50-127, source/pmMethod.cpp:97-105):
  * out[0]=PE out[1]=KE out[2..4]=momentum out[5..7]=angular momentum out[8..10]=total external force
  * (original units; momentum uses the integer-step velocity v + a/2). */

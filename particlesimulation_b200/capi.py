@@ -57,6 +57,7 @@ SYMBOLS = [
     "p3m_green_init", "p3m_set_green_table", "p3m_set_green_table_f64", "p3m_get_green_table",
     "p3m_bin_sort", "p3m_deposit", "p3m_poisson", "p3m_gradient", "p3m_gather", "p3m_short_range",
     "p3m_force", "p3m_kick", "p3m_drift", "p3m_step", "p3m_escaped", "p3m_diagnostics",
+    "p3m_add_acceleration", "p3m_fft3d_c2c",
     "p3m_get_density", "p3m_get_potential", "p3m_get_field", "p3m_get_density_f64",
     "p3m_get_potential_f64", "p3m_set_density", "p3m_set_potential", "p3m_get_cells",
     "p3m_get_chaining_dims", "p3m_chaining_neighbors", "p3m_get_acc_parts", "p3m_get_sr_table",
@@ -93,6 +94,8 @@ def lib():
                      "p3m_get_sr_table", "p3m_get_chaining_dims", "p3m_escaped"):
             getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
         L.p3m_get_cells.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.p3m_add_acceleration.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.p3m_fft3d_c2c.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.p3m_get_acc_parts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.p3m_get_pair_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.p3m_get_phase_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -114,6 +117,15 @@ def default_params() -> P3MParams:
     p = P3MParams()
     lib().p3m_default_params(C.byref(p))
     return p
+
+
+def fft3d_c2c(x, inverse=False):
+    """FFTAdapter contract on a (nz, ny, nx) complex64 array."""
+    x = np.ascontiguousarray(x, np.complex64)
+    out = np.empty_like(x)
+    nz, ny, nx = x.shape
+    _check(lib().p3m_fft3d_c2c(nz, ny, nx, _p(x), _p(out), int(inverse)))
+    return out
 
 
 def chaining_neighbors(dims, cell):
@@ -204,6 +216,9 @@ class Context:
         e = C.c_int(0)
         _check(lib().p3m_escaped(self._h, C.byref(e)))
         return bool(e.value)
+
+    def add_acceleration(self, acc, units=UNITS_ORIGINAL):
+        _check(lib().p3m_add_acceleration(self._h, _p(np.ascontiguousarray(acc, np.float32)), units))
 
     def diagnostics(self):
         d = np.zeros(11, np.float64)

@@ -284,6 +284,36 @@ int get_cells(p3m_ctx* c, int32_t* mesh_cell, int32_t* chain_cell, int32_t* orde
   return 0;
 }
 
+// acc[i] += a[id[i]]  (host-callback external field, include/unitConversions.h:22-24 for the units)
+template <typename T>
+__global__ void k_add_acc(V4<T>* __restrict__ acc, const int* __restrict__ id, long long n,
+                          const float* __restrict__ a, int units, T H, T DT) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long j = id[i];
+  T ax = (T)a[3 * j], ay = (T)a[3 * j + 1], az = (T)a[3 * j + 2];
+  if (units == P3M_UNITS_ORIGINAL) ax = DT * DT * ax / H, ay = DT * DT * ay / H, az = DT * DT * az / H;
+  V4<T> v = acc[i];
+  v.x += ax, v.y += ay, v.z += az;
+  acc[i] = v;
+}
+
+template <typename T>
+int add_acceleration(p3m_ctx* c, const float* a, int units) {
+  State<T>& s = Sel<T>::st(c);
+  const Geom<T>& g = Sel<T>::g(c);
+  const long long n = c->n;
+  if (n == 0) return 0;
+  float* stage = nullptr;
+  P3M_CUDA(cudaMallocAsync((void**)&stage, sizeof(float) * 3 * (size_t)n, c->stream));
+  P3M_CUDA(cudaMemcpyAsync(stage, a, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+  k_add_acc<T><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(s.acc, s.id, n, stage, units, g.H, g.DT);
+  P3M_LAUNCH_CHECK(c);
+  P3M_CUDA(cudaFreeAsync(stage, c->stream));
+  P3M_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 template <typename T>
 void free_state(p3m_ctx* c) {
   State<T>& s = Sel<T>::st(c);
@@ -307,6 +337,7 @@ void free_state(p3m_ctx* c) {
   template int download_particles<T, double>(p3m_ctx*, double*, double*, double*, int);          \
   template int bin_sort<T>(p3m_ctx*);                                                            \
   template int get_cells<T>(p3m_ctx*, int32_t*, int32_t*, int32_t*);                             \
+  template int add_acceleration<T>(p3m_ctx*, const float*, int);                                 \
   template void free_state<T>(p3m_ctx*);
 INST(float)
 INST(double)

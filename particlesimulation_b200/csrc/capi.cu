@@ -338,6 +338,17 @@ int p3m_escaped(p3m_ctx* c, int* escaped) {
   return c->f64 ? escaped_now<double>(c, escaped) : escaped_now<float>(c, escaped);
 }
 
+int p3m_add_acceleration(p3m_ctx* c, const float* a, int units) {
+  CHECK_CTX(c);
+  if (!a) return fail(P3M_EINVAL, "null acceleration array");
+  if (!c->have_particles) return fail(P3M_ESTATE, "no particles set");
+  return P3M_DISPATCH(c, add_acceleration, a, units);
+}
+
+int p3m_fft3d_c2c(int nz, int ny, int nx, const float* in, float* out, int inverse) {
+  return fft3d_c2c(nz, ny, nx, in, out, inverse);
+}
+
 int p3m_diagnostics(p3m_ctx* c, double out[11]) {
   CHECK_CTX(c);
   return P3M_DISPATCH(c, diagnostics, out);

