@@ -1,0 +1,3 @@
+// forwarding header: the reference API of include/simInfo.h lives in particle_simulation_b200.hpp
+#pragma once
+#include "particle_simulation_b200.hpp"
