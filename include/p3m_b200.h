@@ -174,6 +174,10 @@ int p3m_set_potential(p3m_ctx* ctx, const float* mesh);
  * chaining-mesh cell (or -1 for PM-only), and `order` = particle ids in sorted order. */
 int p3m_get_cells(p3m_ctx* ctx, int32_t* mesh_cell, int32_t* chain_cell, int32_t* order);
 int p3m_get_chaining_dims(p3m_ctx* ctx, int32_t dims[3]);
+/* sort geometry after p3m_bin_sort: out = {binning cells x, y, z, Morton bits per axis, sub-cell bits
+ * per axis, particle-id bits, tile block shift, p3m}.  The sort order is ascending in
+ * (Morton(binning cell), Morton(sub-cell), particle id). */
+int p3m_get_binning(p3m_ctx* ctx, int32_t out[8]);
 /* ChainingMesh::getNeighborsAndSelf (source/chainingMesh.cpp:60-84): host-side geometry helper */
 int p3m_chaining_neighbors(const int32_t dims[3], int32_t cell, int32_t out14[14]);
 /* mesh part of the acceleration and short-range acceleration (= total SR force / mass), code units */

@@ -60,7 +60,7 @@ SYMBOLS = [
     "p3m_add_acceleration", "p3m_fft3d_c2c",
     "p3m_get_density", "p3m_get_potential", "p3m_get_field", "p3m_get_density_f64",
     "p3m_get_potential_f64", "p3m_set_density", "p3m_set_potential", "p3m_get_cells",
-    "p3m_get_chaining_dims", "p3m_chaining_neighbors", "p3m_get_acc_parts", "p3m_get_sr_table",
+    "p3m_get_chaining_dims", "p3m_get_binning", "p3m_chaining_neighbors", "p3m_get_acc_parts", "p3m_get_sr_table",
     "p3m_get_phase_ms", "p3m_phase_name", "p3m_get_pair_counts", "p3m_launch_count", "p3m_stream",
     "p3m_synchronize",
 ]
@@ -91,7 +91,7 @@ def lib():
         for name in ("p3m_set_green_table", "p3m_set_green_table_f64", "p3m_get_green_table",
                      "p3m_get_density", "p3m_get_potential", "p3m_get_field", "p3m_get_density_f64",
                      "p3m_get_potential_f64", "p3m_set_density", "p3m_set_potential", "p3m_diagnostics",
-                     "p3m_get_sr_table", "p3m_get_chaining_dims", "p3m_escaped"):
+                     "p3m_get_sr_table", "p3m_get_chaining_dims", "p3m_get_binning", "p3m_escaped"):
             getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
         L.p3m_get_cells.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.p3m_add_acceleration.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -257,6 +257,11 @@ class Context:
         d = np.zeros(3, np.int32)
         _check(lib().p3m_get_chaining_dims(self._h, _p(d)))
         return d
+
+    def binning(self):
+        d = np.zeros(8, np.int32)
+        _check(lib().p3m_get_binning(self._h, _p(d)))
+        return dict(zip(("mx", "my", "mz", "mbits", "sbits", "idbits", "bshift", "p3m"), (int(v) for v in d)))
 
     def acc_parts(self):
         n = self.n

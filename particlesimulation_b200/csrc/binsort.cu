@@ -37,6 +37,7 @@ int alloc_particles(p3m_ctx* c, long long n) {
   P3M_TRY(dev_alloc(&s.keys_alt, cap));
   P3M_TRY(dev_alloc(&s.slots, cap));
   P3M_TRY(dev_alloc(&s.slots_alt, cap));
+  P3M_TRY(dev_alloc(&s.aabb, 2 * (cap / kPPTile + 2)));
   P3M_TRY(dev_alloc(&s.pp_items, 2 * (cap / kPPTargets + ((size_t)1 << (3 * Sel<T>::g(c).mbits)) + 16)));
   size_t tmp = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tmp, s.keys, s.keys_alt, s.slots, s.slots_alt, (int)cap, 0,
@@ -167,6 +168,15 @@ __global__ void k_keys(const V4<T>* __restrict__ posm, const int* __restrict__ i
   bin_cell(g, p.x, p.y, p.z, cx, cy, cz, inside);
   if (!inside) flags[1] = 1;
   uint64_t m = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+  if (g.sbits) {
+    // position inside the chaining cell in units of 1/2^sbits of the cell: x/HC - cx is exact in
+    // floating point (cx is the truncation of the same quotient), so the sub-cell is reproducible
+    const int S = 1 << g.sbits;
+    int sx = (int)((p.x / g.hcx - (T)cx) * (T)S), sy = (int)((p.y / g.hcy - (T)cy) * (T)S),
+        sz = (int)((p.z / g.hcz - (T)cz) * (T)S);
+    sx = min(max(sx, 0), S - 1), sy = min(max(sy, 0), S - 1), sz = min(max(sz, 0), S - 1);
+    m = (m << (3 * g.sbits)) | morton3((uint32_t)sx, (uint32_t)sy, (uint32_t)sz);
+  }
   keys[i] = (m << g.idbits) | (uint64_t)(uint32_t)id[i];
   slots[i] = (uint32_t)i;
 }
@@ -201,6 +211,33 @@ __global__ void k_cell_start(const uint64_t* __restrict__ keys, long long n, int
   cell_start[c] = (int)lo;
 }
 
+// bounding box of every globally aligned tile of kPPTile consecutive (sorted) particles: one warp per
+// tile, 8 coalesced 128-bit loads per lane.  Consumed by the short-range kernel to skip source tiles
+// that cannot reach a target group.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_tile_aabb(const V4<T>* __restrict__ posm, long long n, V4<T>* __restrict__ aabb) {
+  const long long tile = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long b = tile * kPPTile;
+  if (b >= n) return;
+  T lx = 1e30, ly = 1e30, lz = 1e30, hx = -1e30, hy = -1e30, hz = -1e30;
+  for (int k = lane; k < kPPTile && b + k < n; k += 32) {
+    const V4<T> p = posm[b + k];
+    lx = min(lx, p.x), ly = min(ly, p.y), lz = min(lz, p.z);
+    hx = max(hx, p.x), hy = max(hy, p.y), hz = max(hz, p.z);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lx = min(lx, __shfl_xor_sync(0xffffffffu, lx, o)), ly = min(ly, __shfl_xor_sync(0xffffffffu, ly, o));
+    lz = min(lz, __shfl_xor_sync(0xffffffffu, lz, o)), hx = max(hx, __shfl_xor_sync(0xffffffffu, hx, o));
+    hy = max(hy, __shfl_xor_sync(0xffffffffu, hy, o)), hz = max(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+  }
+  if (lane == 0) {
+    aabb[2 * tile] = V4<T>{lx, ly, lz, 0};
+    aabb[2 * tile + 1] = V4<T>{hx, hy, hz, 0};
+  }
+}
+
 template <typename T>
 int bin_sort(p3m_ctx* c) {
   if (!c->have_particles) return fail(P3M_ESTATE, "p3m_bin_sort: no particles set");
@@ -210,6 +247,12 @@ int bin_sort(p3m_ctx* c) {
   int idbits = 1;
   while ((1LL << idbits) < n) ++idbits;
   g.idbits = idbits;
+  g.sbits = 0;
+  if (g.p3m) {
+    g.sbits = kSubBits;
+    while (g.sbits > 0 && 3 * g.mbits + 3 * g.sbits + idbits > 62) --g.sbits;
+  }
+  const int keybits = idbits + 3 * g.sbits + 3 * g.mbits;
   const long long ncells = 1LL << (3 * g.mbits);
   phase_begin(c, PH_BINSORT);
   if (n > 0) {
@@ -218,16 +261,21 @@ int bin_sort(p3m_ctx* c) {
     P3M_LAUNCH_CHECK(c);
     size_t tmp = s.cub_tmp_bytes;
     P3M_CUDA(cub::DeviceRadixSort::SortPairs(s.cub_tmp, tmp, s.keys, s.keys_alt, s.slots, s.slots_alt,
-                                             (int)n, 0, idbits + 3 * g.mbits, c->stream));
-    c->launches += (idbits + 3 * g.mbits + 7) / 8 + 1;
+                                             (int)n, 0, keybits, c->stream));
+    c->launches += (keybits + 7) / 8 + 1;
     k_permute<T><<<blocks, 256, 0, c->stream>>>(s.slots_alt, n, s.posm, s.vel, s.id, s.posm_alt,
                                                 s.vel_alt, s.id_alt);
     P3M_LAUNCH_CHECK(c);
     std::swap(s.posm, s.posm_alt);
     std::swap(s.vel, s.vel_alt);
     std::swap(s.id, s.id_alt);
+    if (g.p3m) {
+      const long long tiles = (n + kPPTile - 1) / kPPTile;
+      k_tile_aabb<T><<<(unsigned)((tiles * 32 + 255) / 256), 256, 0, c->stream>>>(s.posm, n, s.aabb);
+      P3M_LAUNCH_CHECK(c);
+    }
   }
-  k_cell_start<<<(unsigned)((ncells + 1 + 255) / 256), 256, 0, c->stream>>>(s.keys_alt, n, idbits,
+  k_cell_start<<<(unsigned)((ncells + 1 + 255) / 256), 256, 0, c->stream>>>(s.keys_alt, n, idbits + 3 * g.sbits,
                                                                            ncells, s.cell_start);
   P3M_LAUNCH_CHECK(c);
   phase_end(c, PH_BINSORT);
@@ -319,7 +367,7 @@ void free_state(p3m_ctx* c) {
   State<T>& s = Sel<T>::st(c);
   void* ptrs[] = {s.posm,   s.posm_alt,  s.vel,      s.vel_alt,  s.acc,        s.acc_sr,  s.id,
                   s.id_alt, s.keys,      s.keys_alt, s.slots,    s.slots_alt,  s.cub_tmp, s.cell_start,
-                  s.density, s.potential, s.spectrum, s.green,    s.field,      s.sr_table, s.pp_items,
+                  s.density, s.potential, s.spectrum, s.green,    s.field,      s.sr_table, s.pp_items, s.aabb,
                   s.pp_counters, s.pair_counts, s.flags, s.diag};
   for (void* p : ptrs)
     if (p) cudaFree(p);

@@ -50,6 +50,7 @@ static int setup_geometry(p3m_ctx* c) {
   g.unit_roundtrip = p.unit_roundtrip;
   g.tile_shift = kPmTileShift;
   g.idbits = 1;
+  g.sbits = 0;
   if (p.p3m) {
     // ChainingMesh::ChainingMesh, source/chainingMesh.cpp:10-15
     const T box[3] = {(T)p.box[0], (T)p.box[1], (T)p.box[2]};
@@ -407,6 +408,20 @@ int p3m_get_chaining_dims(p3m_ctx* c, int32_t dims[3]) {
   dims[0] = c->f64 ? c->g64.mx : c->g32.mx;
   dims[1] = c->f64 ? c->g64.my : c->g32.my;
   dims[2] = c->f64 ? c->g64.mz : c->g32.mz;
+  return 0;
+}
+
+int p3m_get_binning(p3m_ctx* c, int32_t out[8]) {
+  if (!c || !out) return fail(P3M_EINVAL, "null argument");
+  if (c->f64) {
+    const Geom<double>& g = c->g64;
+    const int32_t v[8] = {g.mx, g.my, g.mz, g.mbits, g.sbits, g.idbits, g.bshift, g.p3m};
+    memcpy(out, v, sizeof(v));
+  } else {
+    const Geom<float>& g = c->g32;
+    const int32_t v[8] = {g.mx, g.my, g.mz, g.mbits, g.sbits, g.idbits, g.bshift, g.p3m};
+    memcpy(out, v, sizeof(v));
+  }
   return 0;
 }
 

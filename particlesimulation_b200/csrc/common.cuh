@@ -54,6 +54,8 @@ struct Geom {
   int mx, my, mz;   // binning cells per axis
   int mbits;        // Morton bits per axis: 2^mbits >= max(mx,my,mz)
   int idbits;       // bits of the particle id packed under the Morton code in the sort key
+  int sbits;        // sub-cell bits per axis sorted between the cell code and the id (P3M: groups
+                    // particles spatially INSIDE a chaining cell so short-range tiles are compact)
   T hcx, hcy, hcz;  // chaining cell size in code units (source/chainingMesh.cpp:13-15)
   int tile_shift;   // PM only: binning cell = (1 << tile_shift)^3 mesh cells
   // deposit / gather tile: an aligned block of (1 << bshift)^3 binning cells, contiguous in key order
@@ -172,5 +174,7 @@ constexpr int kMaxTileBytes = 12288; // per-warp deposit tile budget
 constexpr int kSRTable = 500;        // tabulatedValuesCnt (source/p3mMethod.cpp:42)
 constexpr int kDenseCell = 64;       // chaining cells with >= this many particles use the tiled PP kernel
 constexpr int kPPTargets = 256;      // targets per tiled-PP work item (2 per thread, 128 threads)
+constexpr int kPPTile = 256;         // particles per bounding-boxed source tile (globally aligned)
+constexpr int kSubBits = 3;          // 8^3 sub-cells per chaining cell in the sort key
 
 }  // namespace p3m

@@ -28,6 +28,7 @@ struct State {
   void* cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
   int* cell_start = nullptr;  // (1 << 3*mbits) + 1 entries
+  V4<T>* aabb = nullptr;      // 2 per kPPTile-particle tile: (lo.xyz, -), (hi.xyz, -)
   // meshes
   T* density = nullptr;    // M
   T* potential = nullptr;  // M

@@ -13,18 +13,23 @@
 // acceleration mj * f(r) * r_ij is accumulated directly (the reference's  mi*mj*f / mi).
 //
 //   dense cells (>= kDenseCell particles; the Plummer core puts ~half of all particles in 8 cells):
-//     work item = (cell, 256 consecutive targets), 128 threads x 2 targets in registers; the
-//     neighbour cells' particles are streamed through a shared-memory tile and read back with
-//     broadcast LDS.128; items are generated on the device, sorted by cost (heaviest first) and
-//     pulled from an atomic queue by a persistent grid, so the O(n_cell^2) core does not serialise
-//     on a few CTAs.
+//     work item = (cell, 256 consecutive targets), 128 threads x 2 targets in registers.  Particles are
+//     sorted by (cell, 8^3 sub-cell, id), so 256 consecutive particles are spatially compact; every
+//     globally aligned 256-particle tile carries a bounding box (k_tile_aabb) and a source tile whose
+//     box is farther than the cutoff from the target group's box is skipped WHOLE (this is exact: it
+//     only drops pairs with r >= re).  Surviving tiles are staged in shared memory and read back with
+//     broadcast LDS.128.  Items are generated on the device, sorted by cost (heaviest first) and
+//     pulled from an atomic queue by a persistent grid.
 //   sparse cells: one thread per target walks its 27 cells straight from L1/L2.
 //
 // Force law (code units, G = 1/(4 pi)): table mode reproduces shortRangeForceFromTable
 // (:240-245): linear interpolation in r^2 over 500 entries, multiplied by r_ij (NOT the unit vector,
-// SURVEY Q7); the cutoff test r^2 >= re^2 (:258) is folded into the lookup by clamping xi to 499,
-// whose entry is (0, 0).  r = 0 contributes exactly 0 (F[0] = 0), so i == j needs no test.
-// FP32 pipe bound: ~19 instructions per examined pair.
+// SURVEY Q7).  Inner loop, per pair: 3 FADD (d: exact for close pairs, as in the reference), FMUL +
+// 2 FFMA (r^2), FMUL (xi = r^2 / delta^2), FMNMX (clamp to 499: entry 499 is (0,0), which folds the
+// cutoff test r^2 >= re^2 of :258 into the lookup), FADD.RZ with 2^23 (floor(xi) lands in the
+// mantissa), LEA, LDS.64 of (A_t, B_t) = (F_t - t dF_t, dF_t), FFMA (f = A + B xi), FMUL (mj), 3 FFMA
+// (accumulate) = 16 issue slots.  r = 0 contributes exactly 0 (F_0 = 0), so i == j needs no test.
+// Bound: FP32 / issue rate, not memory.
 #include <cub/device/device_radix_sort.cuh>
 
 #include <cmath>
@@ -57,6 +62,14 @@ __device__ __forceinline__ T ref_force_dev(const SRParams<T>& sp, T r) {
   return G / (r * r);
 }
 
+// table slot of a clamped coordinate 0 <= xi <= 499
+__device__ __forceinline__ int table_slot(float xi) {
+  // round-toward-zero add of 2^23 leaves floor(xi) in the low mantissa bits
+  return __float_as_int(__fadd_rz(xi, 8388608.0f)) - 0x4B000000;
+}
+__device__ __forceinline__ int table_slot(double xi) { return (int)xi; }
+
+// One target-source pair, d = target - source in code units.
 template <typename T, bool TABLE, bool COUNT>
 __device__ __forceinline__ void pair_acc(T dx, T dy, T dz, T mj, const SRParams<T>& sp,
                                          const V2<T>* __restrict__ tab, T& ax, T& ay, T& az,
@@ -65,9 +78,8 @@ __device__ __forceinline__ void pair_acc(T dx, T dy, T dz, T mj, const SRParams<
   if (COUNT) n_in += (r2 < sp.re2 && r2 > T(0)) ? 1u : 0u;
   if (TABLE) {
     const T xi = fmin(r2 * sp.inv_delta2, T(kSRTable - 1));
-    const int t = (int)xi;
-    const V2<T> e = tab[t];
-    const T f = mj * (e.x + (xi - (T)t) * e.y);
+    const V2<T> e = tab[table_slot(xi)];
+    const T f = mj * (e.x + e.y * xi);
     ax += f * dx, ay += f * dy, az += f * dz;
   } else {
     if (r2 < sp.re2 && r2 > T(0)) {  // shortRangeForce :220-238, divided by mi
@@ -118,16 +130,18 @@ __global__ void k_pp_items(const int* __restrict__ cell_start, Geom<T> g, int* _
 template <typename T, bool TABLE, bool COUNT>
 __global__ void __launch_bounds__(128)
 k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
-           const int* __restrict__ items, const unsigned* __restrict__ order,
-           int* __restrict__ counters, Geom<T> g, SRParams<T> sp, const T* __restrict__ g_tab,
-           V4<T>* __restrict__ acc, V4<T>* __restrict__ acc_sr,
+           const V4<T>* __restrict__ aabb, const int* __restrict__ items,
+           const unsigned* __restrict__ order, int* __restrict__ counters, Geom<T> g, SRParams<T> sp,
+           const T* __restrict__ g_tab, V4<T>* __restrict__ acc, V4<T>* __restrict__ acc_sr,
            unsigned long long* __restrict__ pair_counts) {
   __shared__ V2<T> s_tab[kSRTable];
-  __shared__ V4<T> s_src[kPPTargets];
+  __shared__ V4<T> s_src[kPPTile];
+  __shared__ T s_box[4][6];
   __shared__ int s_item;
   load_table(g_tab, s_tab);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nitems = counters[0];
+  const T cut2 = sp.re2 * (T(1) + T(1e-5));
   unsigned long long checked = 0, inrange = 0;
   for (;;) {
     __syncthreads();
@@ -141,7 +155,28 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
     const int tend = min(cell_start[q + 1], t0 + kPPTargets);
     const int i0 = t0 + tid, i1 = t0 + 128 + tid;
     const bool v0 = i0 < tend, v1 = i1 < tend;
-    V4<T> p0 = posm[v0 ? i0 : t0], p1 = posm[v1 ? i1 : t0];
+    const V4<T> p0 = posm[v0 ? i0 : t0], p1 = posm[v1 ? i1 : t0];
+    // bounding box of the target group (code units)
+    {
+      T lx = min(p0.x, p1.x), ly = min(p0.y, p1.y), lz = min(p0.z, p1.z);
+      T hx = max(p0.x, p1.x), hy = max(p0.y, p1.y), hz = max(p0.z, p1.z);
+      for (int o = 16; o > 0; o >>= 1) {
+        lx = min(lx, __shfl_xor_sync(0xffffffffu, lx, o)), ly = min(ly, __shfl_xor_sync(0xffffffffu, ly, o));
+        lz = min(lz, __shfl_xor_sync(0xffffffffu, lz, o)), hx = max(hx, __shfl_xor_sync(0xffffffffu, hx, o));
+        hy = max(hy, __shfl_xor_sync(0xffffffffu, hy, o)), hz = max(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+      }
+      if (lane == 0) {
+        s_box[wid][0] = lx, s_box[wid][1] = ly, s_box[wid][2] = lz;
+        s_box[wid][3] = hx, s_box[wid][4] = hy, s_box[wid][5] = hz;
+      }
+    }
+    __syncthreads();
+    T tlo[3], thi[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      tlo[d] = min(min(s_box[0][d], s_box[1][d]), min(s_box[2][d], s_box[3][d]));
+      thi[d] = max(max(s_box[0][d + 3], s_box[1][d + 3]), max(s_box[2][d + 3], s_box[3][d + 3]));
+    }
     T a0x = 0, a0y = 0, a0z = 0, a1x = 0, a1y = 0, a1z = 0;
     unsigned n_in = 0;
     const int cx = (int)compact3(q), cy = (int)compact3(q >> 1), cz = (int)compact3(q >> 2);
@@ -152,13 +187,21 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
           if (x < 0 || y < 0 || z < 0 || x >= g.mx || y >= g.my || z >= g.mz) continue;
           const uint32_t qn = morton3((uint32_t)x, (uint32_t)y, (uint32_t)z);
           const int s = cell_start[qn], e = cell_start[qn + 1];
-          for (int base = s; base < e; base += kPPTargets) {
+          if (s >= e) continue;
+          for (int tile = s / kPPTile; tile <= (e - 1) / kPPTile; ++tile) {
+            // exact culling: box-box distance beyond the cutoff => no pair of this tile is in range
+            const V4<T> blo = aabb[2 * tile], bhi = aabb[2 * tile + 1];
+            const T gx = max(T(0), max(blo.x - thi[0], tlo[0] - bhi.x));
+            const T gy = max(T(0), max(blo.y - thi[1], tlo[1] - bhi.y));
+            const T gz = max(T(0), max(blo.z - thi[2], tlo[2] - bhi.z));
+            if (gx * gx + gy * gy + gz * gz > cut2) continue;  // CTA-uniform
+            const int jb = max(s, tile * kPPTile), je = min(e, (tile + 1) * kPPTile);
             __syncthreads();
-            const int j0 = base + tid, j1 = base + 128 + tid;
-            if (j0 < e) s_src[tid] = posm[j0];
-            if (j1 < e) s_src[tid + 128] = posm[j1];
+            const int j0 = jb + tid, j1 = jb + 128 + tid;
+            if (j0 < je) s_src[tid] = posm[j0];
+            if (j1 < je) s_src[tid + 128] = posm[j1];
             __syncthreads();
-            const int cnt = min(kPPTargets, e - base);
+            const int cnt = je - jb;
             if (COUNT) checked += (unsigned long long)cnt * ((v0 ? 1 : 0) + (v1 ? 1 : 0));
 #pragma unroll 4
             for (int j = 0; j < cnt; ++j) {
@@ -185,7 +228,6 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
     if (COUNT) inrange += n_in;
   }
   if (COUNT) {
-    // self pairs are examined by the reference too (i == j returns early), so only subtract nothing
     atomicAdd(&pair_counts[0], checked);
     atomicAdd(&pair_counts[1], inrange);
   }
@@ -285,8 +327,15 @@ int sr_table_upload(p3m_ctx* c) {
   std::vector<T> F;
   build_table_host<T>(c, sp, delta2, eps, F);
   c->sr_table_host.assign(F.begin(), F.end());
+  // device layout: slope-intercept form of the reference's interpolation, evaluated in double:
+  //   F_t + (xi - t)(F_{t+1} - F_t)  =  A_t + B_t xi,   A_t = F_t - t B_t,  B_t = F_{t+1} - F_t
+  // entry 499 = (0, 0): everything at or beyond the cutoff evaluates to zero.
   std::vector<T> pairs(2 * kSRTable);
-  for (int t = 0; t < kSRTable - 1; ++t) pairs[2 * t] = F[t], pairs[2 * t + 1] = F[t + 1] - F[t];
+  for (int t = 0; t < kSRTable - 1; ++t) {
+    const double b = (double)F[t + 1] - (double)F[t];
+    pairs[2 * t] = (T)((double)F[t] - t * b);
+    pairs[2 * t + 1] = (T)b;
+  }
   pairs[2 * (kSRTable - 1)] = 0, pairs[2 * (kSRTable - 1) + 1] = 0;
   P3M_CUDA(cudaMemcpyAsync(s.sr_table, pairs.data(), sizeof(T) * 2 * kSRTable, cudaMemcpyHostToDevice,
                            c->stream));
@@ -309,7 +358,7 @@ static int run_pp(p3m_ctx* c) {
   const long long ncells = 1LL << (3 * g.mbits);
   // upper bound on dense-cell work items: every dense cell holds >= kDenseCell particles
   long long max_items = n / kPPTargets + (ncells < n / kDenseCell ? ncells : n / kDenseCell) + 16;
-  unsigned* cost = reinterpret_cast<unsigned*>(s.keys);          // 8 B * cap available
+  unsigned* cost = reinterpret_cast<unsigned*>(s.keys);  // sort scratch is free between bin_sort calls
   unsigned* cost_sorted = reinterpret_cast<unsigned*>(s.keys_alt);
   unsigned* idx = s.slots;
   unsigned* order = s.slots_alt;
@@ -326,8 +375,8 @@ static int run_pp(p3m_ctx* c) {
                                                      (int)max_items, 0, 32, c->stream));
   c->launches += 5;
   k_pp_tiled<T, TABLE, COUNT><<<c->num_sms * 8, 128, 0, c->stream>>>(
-      s.posm, s.cell_start, s.pp_items, order, s.pp_counters, g, sp, s.sr_table, s.acc, s.acc_sr,
-      s.pair_counts);
+      s.posm, s.cell_start, s.aabb, s.pp_items, order, s.pp_counters, g, sp, s.sr_table, s.acc,
+      s.acc_sr, s.pair_counts);
   P3M_LAUNCH_CHECK(c);
   k_pp_sparse<T, TABLE, COUNT><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(
       s.posm, n, s.cell_start, g, sp, s.sr_table, s.acc, s.acc_sr, s.pair_counts);

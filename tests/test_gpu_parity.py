@@ -44,6 +44,7 @@ def test_cells_and_sort_order_bit_exact(n, p3m):
         mc, cc, order = ctx.cells()
         gpos, _, _ = ctx.get_particles(capi.UNITS_CODE)
         gdims = ctx.chaining_dims() if p3m else None
+        sbits = ctx.binning()["sbits"]
     assert np.array_equal(gpos, pc), "code-unit positions must be bit-identical to the reference's"
     # PM mesh cell: (int)pos, flat x + y*Nx + z*Nx*Ny  (source/pmMethod.cpp:250-252)
     t = pc.astype(np.int32)  # truncation, positions are positive
@@ -57,8 +58,18 @@ def test_cells_and_sort_order_bit_exact(n, p3m):
         assert np.all(cc == -1)
         cx, cy, cz = t[:, 0] >> 3, t[:, 1] >> 3, t[:, 2] >> 3
     key = morton3(cx, cy, cz)
+    if sbits:
+        # sub-cell inside the chaining cell, fp32 arithmetic as on the device
+        f32 = np.float32
+        hc = [f32(f32(f32(p.box[d]) / f32(dims[d])) / f32(p.H)) for d in range(3)]
+        S = 1 << sbits
+        sub = [np.clip(((pc[:, d] / hc[d] - c.astype(f32)) * f32(S)).astype(np.int32), 0, S - 1)
+               for d, c in enumerate((cx, cy, cz))]
+        key = (key << np.uint64(3 * sbits)) | morton3(*sub)
+    else:
+        assert not p3m
     expect = np.lexsort((np.arange(n), key))  # stable: ties broken by particle id
-    assert np.array_equal(order, expect.astype(np.int32)), "sort order must be (z-order cell, id)"
+    assert np.array_equal(order, expect.astype(np.int32)), "sort order must be (z-order cell, sub-cell, id)"
 
 
 def test_sort_is_idempotent_and_deterministic():
