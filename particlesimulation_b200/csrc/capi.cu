@@ -173,6 +173,14 @@ int p3m_create(const p3m_params* prm, p3m_ctx** out) {
   P3M_CUDA(cudaGetDeviceProperties(&prop, dev));
   c->num_sms = prop.multiProcessorCount;
   P3M_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {
+    // staging buffers come from the stream-ordered pool: keep freed blocks cached across synchronisations
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   memset(&c->timer, 0, sizeof(c->timer));
   for (int i = 0; i < P3M_NPHASE; ++i) {
     cudaEventCreate(&c->timer.a[i]);

@@ -62,23 +62,47 @@ __device__ __forceinline__ T ref_force_dev(const SRParams<T>& sp, T r) {
   return G / (r * r);
 }
 
-// table slot of a clamped coordinate 0 <= xi <= 499
-__device__ __forceinline__ int table_slot(float xi) {
-  // round-toward-zero add of 2^23 leaves floor(xi) in the low mantissa bits
-  return __float_as_int(__fadd_rz(xi, 8388608.0f)) - 0x4B000000;
-}
-__device__ __forceinline__ int table_slot(double xi) { return (int)xi; }
+// Handle of the shared-memory table of (A_t, B_t) pairs.
+// fp32: a round-toward-zero add of 2^23 leaves floor(xi) in the low mantissa bits; the exponent bits
+// (0x4B000000) are folded into an opaque pre-biased base, so the lookup is FADD.RZ + LEA + LDS.64.
+template <typename T>
+struct TableRef;
+template <>
+struct TableRef<float> {
+  unsigned base;
+  // `slot` is a shared-memory word: the biased base makes a round trip through it so that ptxas cannot
+  // re-associate the bias back out of the address arithmetic (it would cost an IADD3 per pair).
+  // Must be called by all threads of the block, before a __syncthreads().
+  __device__ __forceinline__ TableRef(const V2<float>* tab, volatile unsigned* slot) {
+    if (threadIdx.x == 0) *slot = (unsigned)__cvta_generic_to_shared(tab) - (0x4B000000u << 3);
+    base = 0;
+  }
+  __device__ __forceinline__ void finish(volatile unsigned* slot) { base = *slot; }
+  __device__ __forceinline__ V2<float> get(float xi) const {  // 0 <= xi <= 499
+    const unsigned addr = base + ((unsigned)__float_as_int(__fadd_rz(xi, 8388608.0f)) << 3);
+    V2<float> e;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(e.x), "=f"(e.y) : "r"(addr));
+    return e;
+  }
+};
+template <>
+struct TableRef<double> {
+  const V2<double>* tab;
+  __device__ __forceinline__ TableRef(const V2<double>* t, volatile unsigned*) : tab(t) {}
+  __device__ __forceinline__ void finish(volatile unsigned*) {}
+  __device__ __forceinline__ V2<double> get(double xi) const { return tab[(int)xi]; }
+};
 
 // One target-source pair, d = target - source in code units.
 template <typename T, bool TABLE, bool COUNT>
 __device__ __forceinline__ void pair_acc(T dx, T dy, T dz, T mj, const SRParams<T>& sp,
-                                         const V2<T>* __restrict__ tab, T& ax, T& ay, T& az,
+                                         const TableRef<T>& tab, T& ax, T& ay, T& az,
                                          unsigned& n_in) {
   const T r2 = dx * dx + dy * dy + dz * dz;
   if (COUNT) n_in += (r2 < sp.re2 && r2 > T(0)) ? 1u : 0u;
   if (TABLE) {
     const T xi = fmin(r2 * sp.inv_delta2, T(kSRTable - 1));
-    const V2<T> e = tab[table_slot(xi)];
+    const V2<T> e = tab.get(xi);
     const T f = mj * (e.x + e.y * xi);
     ax += f * dx, ay += f * dy, az += f * dz;
   } else {
@@ -138,7 +162,11 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
   __shared__ V4<T> s_src[kPPTile];
   __shared__ T s_box[4][6];
   __shared__ int s_item;
+  __shared__ unsigned s_tb;
   load_table(g_tab, s_tab);
+  TableRef<T> tref(s_tab, &s_tb);
+  __syncthreads();
+  tref.finish(&s_tb);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nitems = counters[0];
   const T cut2 = sp.re2 * (T(1) + T(1e-5));
@@ -207,9 +235,9 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
             for (int j = 0; j < cnt; ++j) {
               const V4<T> sj = s_src[j];
               unsigned c0 = 0, c1 = 0;
-              pair_acc<T, TABLE, COUNT>(p0.x - sj.x, p0.y - sj.y, p0.z - sj.z, sj.w, sp, s_tab, a0x,
+              pair_acc<T, TABLE, COUNT>(p0.x - sj.x, p0.y - sj.y, p0.z - sj.z, sj.w, sp, tref, a0x,
                                         a0y, a0z, c0);
-              pair_acc<T, TABLE, COUNT>(p1.x - sj.x, p1.y - sj.y, p1.z - sj.z, sj.w, sp, s_tab, a1x,
+              pair_acc<T, TABLE, COUNT>(p1.x - sj.x, p1.y - sj.y, p1.z - sj.z, sj.w, sp, tref, a1x,
                                         a1y, a1z, c1);
               if (COUNT) n_in += (v0 ? c0 : 0u) + (v1 ? c1 : 0u);
             }
@@ -239,8 +267,11 @@ k_pp_sparse(const V4<T>* __restrict__ posm, long long n, const int* __restrict__
             Geom<T> g, SRParams<T> sp, const T* __restrict__ g_tab, V4<T>* __restrict__ acc,
             V4<T>* __restrict__ acc_sr, unsigned long long* __restrict__ pair_counts) {
   __shared__ V2<T> s_tab[kSRTable];
+  __shared__ unsigned s_tb;
   load_table(g_tab, s_tab);
+  TableRef<T> tref(s_tab, &s_tb);
   __syncthreads();
+  tref.finish(&s_tb);
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const V4<T> p = posm[i];
@@ -262,7 +293,7 @@ k_pp_sparse(const V4<T>* __restrict__ posm, long long n, const int* __restrict__
         if (COUNT) checked += (unsigned long long)(e - s);
         for (int j = s; j < e; ++j) {
           const V4<T> sj = posm[j];
-          pair_acc<T, TABLE, COUNT>(p.x - sj.x, p.y - sj.y, p.z - sj.z, sj.w, sp, s_tab, ax, ay, az,
+          pair_acc<T, TABLE, COUNT>(p.x - sj.x, p.y - sj.y, p.z - sj.z, sj.w, sp, tref, ax, ay, az,
                                     n_in);
         }
       }
