@@ -162,6 +162,26 @@ def c2_particles(n):
     return ics.plummer(n, center=(30.0, 30.0, 30.0), a=2.0, r_max=15.0, M=1.0, G=4.5e-3, seed=42)
 
 
+def multi_params(capi, world, timing=False):
+    """N > 1: one C2 cluster per GPU (weak scaling).  The box and the mesh grow along z with the rank
+    count -- box 60 x 60 x 60 N, mesh 128 x 128 x 128 N -- every other parameter is C2's."""
+    p = c2_params(capi, timing)
+    p.nz = GRID_C2[2] * world
+    p.box[2] = BOX_C2[2] * world
+    return p
+
+
+def multi_particles(world, n_per_gpu):
+    """One Plummer sphere per z-slab, centred in it; every rank builds the same global arrays."""
+    from particlesimulation_b200 import ics
+    pos, vel, mass = [], [], []
+    for r in range(world):
+        a, b, c = ics.plummer(n_per_gpu, center=(30.0, 30.0, 30.0 + 60.0 * r), a=2.0, r_max=15.0, M=1.0, G=4.5e-3,
+                              seed=42 + r)
+        pos.append(a); vel.append(b); mass.append(c)
+    return np.concatenate(pos), np.concatenate(vel), np.concatenate(mass)
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -363,7 +383,106 @@ def run_ours(args):
 
 
 def run_ours_multi(args, rank, world, local):
-    raise SystemExit("bench.py: the multi-GPU z-slab path is not built yet (DESIGN.md section 7); run with --gpus 1")
+    """One process per GPU (torchrun), z-slab decomposition with NCCL inside the library."""
+    import torch
+    import torch.distributed as dist
+
+    from particlesimulation_b200 import capi
+    from particlesimulation_b200 import dist as pdist
+
+    rank, world, local = pdist.init_process_group("nccl")
+    assert world == args.gpus, f"WORLD_SIZE {world} != --gpus {args.gpus}"
+    cu = Cuda()
+    cu.set_device(local)
+    n_per = int(os.environ.get("P3M_BENCH_N", N_C2))
+    pos, vel, mass = multi_particles(world, n_per)
+    n_total = len(mass)
+    prm = multi_params(capi, world)
+    prm.device = local
+    ctx = pdist.create_context(prm, capi)
+    stream = ctx.stream
+    ctx.set_particles(pos, vel, mass)
+    ctx.green_init()
+    ctx.force()
+    ctx.kick(0.5)
+    for _ in range(args.warmup):
+        ctx.step(1)
+    flush_bytes = 256 << 20
+    flush = cu.malloc(flush_bytes)
+    ev = [(cu.event(), cu.event()) for _ in range(args.steps)]
+    launches0 = ctx.launches
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    dist.barrier()
+    cu.sync()
+    for a, b in ev:
+        cu.check(cu.rt.cudaMemsetAsync(flush, 0, flush_bytes, stream), "flush")
+        cu.record(a, stream)
+        ctx.step(1)
+        cu.record(b, stream)
+    cu.sync()
+    dist.barrier()
+    clk = clocks.stop() if rank == 0 else None
+    ms = [cu.elapsed_ms(a, b) for a, b in ev]
+    t = torch.tensor([float(np.sum(ms))], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)  # device time, max over ranks
+    total_ms = float(t.item())
+    launches = ctx.launches - launches0
+    nloc = torch.tensor([ctx.n], device="cuda")
+    nmin, nmax = nloc.clone(), nloc.clone()
+    dist.all_reduce(nmin, op=dist.ReduceOp.MIN)
+    dist.all_reduce(nmax, op=dist.ReduceOp.MAX)
+
+    # end to end: every rank uploads the particles it holds (pinned host buffers, explicit ids), steps,
+    # and reads them back
+    ids, lp, lv, _ = ctx.get_local(capi.UNITS_ORIGINAL)
+    nl = len(ids)
+    hp, hv, hm = cu.pinned((nl + 4096, 3)), cu.pinned((nl + 4096, 3)), cu.pinned((nl + 4096,))
+    hid = cu.pinned((nl + 4096,), np.int32)
+    hp[:nl], hv[:nl], hm[:nl], hid[:nl] = lp, lv, mass[ids], ids
+    e2e_steps = max(2, min(args.steps, 5))
+    h2d = d2h = 0
+    t0 = None
+    for it in range(e2e_steps + 1):
+        if it == 1:
+            dist.barrier(); cu.sync(); t0 = time.time(); h2d = d2h = 0
+        ctx.set_particles_ids(hp[:nl], hv[:nl], hm[:nl], hid[:nl])
+        h2d += 32 * nl
+        ctx.step(1)
+        ids, lp, lv, _ = ctx.get_local(capi.UNITS_ORIGINAL)
+        nl = min(len(ids), hp.shape[0])
+        d2h += 28 * nl
+        hp[:nl], hv[:nl], hm[:nl], hid[:nl] = lp[:nl], lv[:nl], mass[ids[:nl]], ids[:nl]
+    cu.sync(); dist.barrier()
+    te = torch.tensor([time.time() - t0], device="cuda")
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item()) / e2e_steps
+    tb = torch.tensor([float(h2d), float(d2h)], device="cuda")
+    dist.all_reduce(tb)
+    if rank == 0:
+        value = n_total * args.steps / (total_ms / 1e3)
+        line = {
+            "metric": "P3M particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C5-style weak scaling of C2: one P3M Plummer sphere of 2^20 particles per GPU, "
+                                   f"mesh 128x128x{128 * world}, TSC, S1-optimal Green, chaining-mesh PP",
+                       "particles": n_total, "mesh": [GRID_C2[0], GRID_C2[1], GRID_C2[2] * world],
+                       "l2": "256 MiB memset between timed steps (outside the events)",
+                       "parallelism": f"z-slabs of particles over {world} GPUs (NCCL: migration, ghost layers, density all-reduce)",
+                       "particles_per_rank_min_max": [int(nmin.item()), int(nmax.item())]},
+            "clocks": clk, "gpu_launches": launches,
+            "e2e": {"value": n_total / e2e_s, "unit": "particle-steps/s",
+                    "h2d_bytes_per_step": int(tb[0].item() / e2e_steps), "d2h_bytes_per_step": int(tb[1].item() / e2e_steps),
+                    "ms_per_step": e2e_s * 1e3},
+            "roofline": None, "cpu_baseline": None,
+            "note": "roofline and cpu_baseline are reported by the N = 1 run",
+        }
+        print(json.dumps(line))
+    ctx.close()
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def main():

@@ -87,6 +87,30 @@ void p3m_default_params(p3m_params* p);
 int p3m_create(const p3m_params* params, p3m_ctx** out);
 int p3m_destroy(p3m_ctx* ctx);
 
+/* ---- multi-GPU: z-slab decomposition of the particles, one process per GPU, NCCL.
+ * Nothing of this exists in the reference.  Rank 0 obtains an id with p3m_comm_unique_id and hands it
+ * to every rank by any means (bench.py: torch.distributed broadcast); all ranks then call
+ * p3m_create_dist collectively.  Afterwards the SAME calls as on one GPU drive the run (they become
+ * collective): p3m_set_particles takes the full particle set on every rank and keeps this rank's
+ * slab; p3m_force / p3m_step migrate particles, exchange ghost layers and sum the density mesh over
+ * NVLink; id-indexed readbacks fill the entries of the particles the rank holds and leave the rest 0. */
+#define P3M_UNIQUE_ID_BYTES 128
+int p3m_comm_unique_id(void* out_bytes128);
+int p3m_create_dist(const p3m_params* params, const void* unique_id_bytes128, int rank, int nranks,
+                    p3m_ctx** out);
+/* this rank's particles (p3m_num_particles of them) in local order with their global ids */
+int p3m_get_local(p3m_ctx* ctx, int32_t* ids, float* pos, float* vel, float* acc, int units);
+/* upload a subset with explicit global ids (e.g. what p3m_get_local returned); the next force
+ * evaluation migrates whatever does not belong to this rank's slab */
+int p3m_set_particles_ids(p3m_ctx* ctx, const float* pos, const float* vel, const float* mass,
+                          const int32_t* ids, int64_t n, int units);
+int64_t p3m_num_global(const p3m_ctx* ctx);
+/* host-only: the binning layers along z and their cuts for `nranks` ranks (cuts[r]..cuts[r+1] belongs to
+ * rank r); needs no device, identical on every rank.  layers_out = number of layers that are cut. */
+int p3m_slab_cuts(const p3m_params* params, int nranks, int32_t cuts[9], int32_t* layers_out);
+/* out = {rank, nranks, first owned binning layer, one past the last, ghost particles held} */
+int p3m_rank_info(p3m_ctx* ctx, int64_t out[5]);
+
 /* Particle upload.  units = P3M_UNITS_ORIGINAL applies stateToCodeUnits + massToCodeUnits on the
  * device (source/unitConversions.cpp:23-71, include/unitConversions.h:8-50), as the head of run()
  * does (source/pmMethod.cpp:72-73).  vel may be NULL (zeros).  Replaces the constructor's copy of

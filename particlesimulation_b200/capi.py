@@ -53,6 +53,8 @@ _lib = None
 # every symbol include/p3m_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "p3m_last_error", "p3m_version", "p3m_default_params", "p3m_create", "p3m_destroy",
+    "p3m_comm_unique_id", "p3m_create_dist", "p3m_get_local", "p3m_set_particles_ids", "p3m_num_global",
+    "p3m_rank_info", "p3m_slab_cuts",
     "p3m_set_particles", "p3m_get_particles", "p3m_get_particles_f64", "p3m_num_particles",
     "p3m_green_init", "p3m_set_green_table", "p3m_set_green_table_f64", "p3m_get_green_table",
     "p3m_bin_sort", "p3m_deposit", "p3m_poisson", "p3m_gradient", "p3m_gather", "p3m_short_range",
@@ -77,6 +79,13 @@ def lib():
         L.p3m_last_error.restype = C.c_char_p
         L.p3m_phase_name.restype = C.c_char_p
         L.p3m_num_particles.restype = C.c_int64
+        L.p3m_num_global.restype = C.c_int64
+        L.p3m_num_global.argtypes = [C.c_void_p]
+        L.p3m_get_local.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.p3m_set_particles_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+        L.p3m_rank_info.argtypes = [C.c_void_p, C.c_void_p]
+        L.p3m_comm_unique_id.argtypes = [C.c_void_p]
+        L.p3m_create_dist.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.p3m_launch_count.restype = C.c_int64
         L.p3m_stream.restype = C.c_void_p
         for name in ("p3m_num_particles", "p3m_launch_count", "p3m_stream", "p3m_destroy",
@@ -119,6 +128,21 @@ def default_params() -> P3MParams:
     return p
 
 
+def slab_cuts(params, nranks):
+    """Layer cuts of the z-slab decomposition (host only)."""
+    cuts = np.zeros(9, np.int32)
+    layers = C.c_int32(0)
+    _check(lib().p3m_slab_cuts(C.byref(params), int(nranks), _p(cuts), C.byref(layers)))
+    return cuts[: nranks + 1].copy(), int(layers.value)
+
+
+def comm_unique_id() -> bytes:
+    """NCCL unique id (128 bytes) for p3m_create_dist; call on rank 0 and broadcast."""
+    buf = C.create_string_buffer(128)
+    _check(lib().p3m_comm_unique_id(buf))
+    return buf.raw
+
+
 def fft3d_c2c(x, inverse=False):
     """FFTAdapter contract on a (nz, ny, nx) complex64 array."""
     x = np.ascontiguousarray(x, np.complex64)
@@ -138,10 +162,16 @@ def chaining_neighbors(dims, cell):
 class Context:
     """One p3m_ctx.  Thin: every method is one C-ABI call on host numpy buffers."""
 
-    def __init__(self, params: P3MParams):
+    def __init__(self, params: P3MParams, unique_id: bytes | None = None, rank: int = 0, nranks: int = 1):
         self._h = C.c_void_p()
         self.params = params
-        _check(lib().p3m_create(C.byref(params), C.byref(self._h)))
+        self.rank, self.nranks = rank, nranks
+        if nranks > 1:
+            assert unique_id is not None and len(unique_id) == 128
+            uid = C.create_string_buffer(unique_id, 128)
+            _check(lib().p3m_create_dist(C.byref(params), uid, rank, nranks, C.byref(self._h)))
+        else:
+            _check(lib().p3m_create(C.byref(params), C.byref(self._h)))
         self.M = params.nx * params.ny * params.nz
         self.shape = (params.nz, params.ny, params.nx)
 
@@ -166,6 +196,27 @@ class Context:
     def n(self):
         return int(lib().p3m_num_particles(self._h))
 
+    @property
+    def n_global(self):
+        return int(lib().p3m_num_global(self._h))
+
+    def rank_info(self):
+        d = np.zeros(5, np.int64)
+        _check(lib().p3m_rank_info(self._h, _p(d)))
+        return dict(zip(("rank", "nranks", "layer0", "layer1", "ghosts"), (int(v) for v in d)))
+
+    def get_local(self, units=UNITS_ORIGINAL, want=("pos", "vel")):
+        n = self.n
+        ids = np.empty(n, np.int32)
+        out = {k: (np.empty((n, 3), np.float32) if k in want else None) for k in ("pos", "vel", "acc")}
+        _check(lib().p3m_get_local(self._h, _p(ids), _p(out["pos"]), _p(out["vel"]), _p(out["acc"]), units))
+        return ids, out["pos"], out["vel"], out["acc"]
+
+    def set_particles_ids(self, pos, vel, mass, ids, units=UNITS_ORIGINAL):
+        pos = np.ascontiguousarray(pos, np.float32); vel = np.ascontiguousarray(vel, np.float32)
+        mass = np.ascontiguousarray(mass, np.float32); ids = np.ascontiguousarray(ids, np.int32)
+        _check(lib().p3m_set_particles_ids(self._h, _p(pos), _p(vel), _p(mass), _p(ids), len(ids), units))
+
     def set_particles(self, pos, vel, mass, units=UNITS_ORIGINAL):
         pos = np.ascontiguousarray(pos, np.float32)
         mass = np.ascontiguousarray(mass, np.float32)
@@ -175,7 +226,7 @@ class Context:
         _check(lib().p3m_set_particles(self._h, _p(pos), _p(vel), _p(mass), n, units))
 
     def get_particles(self, units=UNITS_CODE, f64=False, want=("pos", "vel", "acc")):
-        n = self.n
+        n = self.n_global
         dt = np.float64 if f64 else np.float32
         out = {k: (np.empty((n, 3), dt) if k in want else None) for k in ("pos", "vel", "acc")}
         fn = lib().p3m_get_particles_f64 if f64 else lib().p3m_get_particles
@@ -248,8 +299,8 @@ class Context:
         _check(lib().p3m_set_potential(self._h, _p(np.ascontiguousarray(phi, np.float32))))
 
     def cells(self):
-        n = self.n
-        mc = np.empty(n, np.int32); cc = np.empty(n, np.int32); order = np.empty(n, np.int32)
+        n = self.n_global
+        mc = np.empty(n, np.int32); cc = np.empty(n, np.int32); order = np.empty(self.n, np.int32)
         _check(lib().p3m_get_cells(self._h, _p(mc), _p(cc), _p(order)))
         return mc, cc, order
 
@@ -264,7 +315,7 @@ class Context:
         return dict(zip(("mx", "my", "mz", "mbits", "sbits", "idbits", "bshift", "p3m"), (int(v) for v in d)))
 
     def acc_parts(self):
-        n = self.n
+        n = self.n_global
         pm = np.empty((n, 3), np.float64); sr = np.empty((n, 3), np.float64)
         _check(lib().p3m_get_acc_parts(self._h, _p(pm), _p(sr)))
         return pm, sr

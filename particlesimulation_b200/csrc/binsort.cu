@@ -9,6 +9,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "ctx.cuh"
+#include "sort_kernels.cuh"
 
 namespace p3m {
 
@@ -100,8 +101,89 @@ int upload_particles(p3m_ctx* c, const float* pos, const float* vel, const float
   }
   P3M_CUDA(cudaFreeAsync(stage, c->stream));
   c->n = n;
+  c->n_global = n;
   c->have_particles = true;
   c->sorted = false;
+  // multi-GPU: every rank was handed the whole set; keep the particles of this rank's z-slab
+  if (c->nranks > 1) P3M_TRY(dist_migrate<T>(c, false));
+  return 0;
+}
+
+// A subset with explicit global ids (multi-GPU end-to-end path: each rank uploads what it holds; the
+// next p3m_bin_sort migrates anything that is not in this rank's slab).
+template <typename T>
+__global__ void k_set_ids(const int32_t* __restrict__ ids, long long n, int* __restrict__ id) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) id[i] = ids[i];
+}
+
+template <typename T>
+int upload_particles_ids(p3m_ctx* c, const float* pos, const float* vel, const float* mass, const int32_t* ids,
+                         long long n, int units) {
+  const long long ng = c->n_global;
+  if (ng <= 0) return fail(P3M_ESTATE, "p3m_set_particles_ids: call p3m_set_particles once first (global count)");
+  if (n > c->cap) return fail(P3M_ERANGE, "subset of %lld particles exceeds the capacity %lld", n, c->cap);
+  const int nr = c->nranks;
+  c->nranks = 1;  // plain upload, no filtering
+  int r = upload_particles<T>(c, pos, vel, mass, n, units);
+  c->nranks = nr;
+  if (r != 0) return r;
+  c->n_global = ng;
+  State<T>& s = Sel<T>::st(c);
+  if (n > 0) {
+    int32_t* stage = nullptr;
+    P3M_CUDA(cudaMallocAsync((void**)&stage, sizeof(int32_t) * (size_t)n, c->stream));
+    P3M_CUDA(cudaMemcpyAsync(stage, ids, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+    k_set_ids<T><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(stage, n, s.id);
+    P3M_LAUNCH_CHECK(c);
+    P3M_CUDA(cudaFreeAsync(stage, c->stream));
+  }
+  return 0;
+}
+
+// local particles in local (sorted) order with their global ids
+template <typename T>
+__global__ void k_download_local(const V4<T>* __restrict__ posm, const V4<T>* __restrict__ vel,
+                                 const V4<T>* __restrict__ acc, long long n, int units, T H, T DT,
+                                 float* __restrict__ pos_o, float* __restrict__ vel_o, float* __restrict__ acc_o) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool orig = units == P3M_UNITS_ORIGINAL;
+  if (pos_o) {
+    V4<T> p = posm[i];
+    if (orig) p.x = H * p.x, p.y = H * p.y, p.z = H * p.z;
+    pos_o[3 * i] = (float)p.x, pos_o[3 * i + 1] = (float)p.y, pos_o[3 * i + 2] = (float)p.z;
+  }
+  if (vel_o) {
+    V4<T> v = vel[i];
+    if (orig) v.x = H * v.x / DT, v.y = H * v.y / DT, v.z = H * v.z / DT;
+    vel_o[3 * i] = (float)v.x, vel_o[3 * i + 1] = (float)v.y, vel_o[3 * i + 2] = (float)v.z;
+  }
+  if (acc_o) {
+    V4<T> a = acc[i];
+    if (orig) a.x = H * a.x / (DT * DT), a.y = H * a.y / (DT * DT), a.z = H * a.z / (DT * DT);
+    acc_o[3 * i] = (float)a.x, acc_o[3 * i + 1] = (float)a.y, acc_o[3 * i + 2] = (float)a.z;
+  }
+}
+
+template <typename T>
+int download_local(p3m_ctx* c, int32_t* ids, float* pos, float* vel, float* acc, int units) {
+  State<T>& s = Sel<T>::st(c);
+  const Geom<T>& g = Sel<T>::g(c);
+  const long long n = c->n;
+  if (n == 0) return 0;
+  float* stage = nullptr;
+  P3M_CUDA(cudaMallocAsync((void**)&stage, sizeof(float) * 9 * (size_t)n, c->stream));
+  k_download_local<T><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+      s.posm, s.vel, s.acc, n, units, g.H, g.DT, pos ? stage : nullptr, vel ? stage + 3 * n : nullptr,
+      acc ? stage + 6 * n : nullptr);
+  P3M_LAUNCH_CHECK(c);
+  if (pos) P3M_CUDA(cudaMemcpyAsync(pos, stage, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+  if (vel) P3M_CUDA(cudaMemcpyAsync(vel, stage + 3 * n, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+  if (acc) P3M_CUDA(cudaMemcpyAsync(acc, stage + 6 * n, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+  if (ids) P3M_CUDA(cudaMemcpyAsync(ids, s.id, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+  P3M_CUDA(cudaFreeAsync(stage, c->stream));
+  P3M_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
@@ -137,14 +219,20 @@ template <typename T, typename O>
 int download_particles(p3m_ctx* c, O* pos, O* vel, O* acc, int units) {
   State<T>& s = Sel<T>::st(c);
   const Geom<T>& g = Sel<T>::g(c);
-  long long n = c->n;
+  // output arrays are indexed by the ORIGINAL (global) particle id; with several ranks each one fills
+  // the entries of the particles it holds and leaves the others zero
+  const long long nl = c->n;
+  const long long n = c->nranks > 1 ? c->n_global : nl;
   if (n == 0) return 0;
   O* stage = nullptr;
   P3M_CUDA(cudaMallocAsync((void**)&stage, sizeof(O) * 9 * (size_t)n, c->stream));
-  k_download<T, O><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
-      s.posm, s.vel, s.acc, s.id, n, units, g.H, g.DT, pos ? stage : nullptr,
-      vel ? stage + 3 * n : nullptr, acc ? stage + 6 * n : nullptr);
-  P3M_LAUNCH_CHECK(c);
+  if (c->nranks > 1) P3M_CUDA(cudaMemsetAsync(stage, 0, sizeof(O) * 9 * (size_t)n, c->stream));
+  if (nl > 0) {
+    k_download<T, O><<<(unsigned)((nl + 255) / 256), 256, 0, c->stream>>>(
+        s.posm, s.vel, s.acc, s.id, nl, units, g.H, g.DT, pos ? stage : nullptr,
+        vel ? stage + 3 * n : nullptr, acc ? stage + 6 * n : nullptr);
+    P3M_LAUNCH_CHECK(c);
+  }
   if (pos) P3M_CUDA(cudaMemcpyAsync(pos, stage, sizeof(O) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
   if (vel)
     P3M_CUDA(cudaMemcpyAsync(vel, stage + 3 * n, sizeof(O) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
@@ -155,97 +243,16 @@ int download_particles(p3m_ctx* c, O* pos, O* vel, O* acc, int units) {
   return 0;
 }
 
-// ---- A0: sort keys ---------------------------------------------------------------------------------
-template <typename T>
-__global__ void k_keys(const V4<T>* __restrict__ posm, const int* __restrict__ id, long long n,
-                       Geom<T> g, uint64_t* __restrict__ keys, uint32_t* __restrict__ slots,
-                       int* __restrict__ flags) {
-  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  V4<T> p = posm[i];
-  int cx, cy, cz;
-  bool inside;
-  bin_cell(g, p.x, p.y, p.z, cx, cy, cz, inside);
-  if (!inside) flags[1] = 1;
-  uint64_t m = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
-  if (g.sbits) {
-    // position inside the chaining cell in units of 1/2^sbits of the cell: x/HC - cx is exact in
-    // floating point (cx is the truncation of the same quotient), so the sub-cell is reproducible
-    const int S = 1 << g.sbits;
-    int sx = (int)((p.x / g.hcx - (T)cx) * (T)S), sy = (int)((p.y / g.hcy - (T)cy) * (T)S),
-        sz = (int)((p.z / g.hcz - (T)cz) * (T)S);
-    sx = min(max(sx, 0), S - 1), sy = min(max(sy, 0), S - 1), sz = min(max(sz, 0), S - 1);
-    m = (m << (3 * g.sbits)) | morton3((uint32_t)sx, (uint32_t)sy, (uint32_t)sz);
-  }
-  keys[i] = (m << g.idbits) | (uint64_t)(uint32_t)id[i];
-  slots[i] = (uint32_t)i;
-}
-
-template <typename T>
-__global__ void k_permute(const uint32_t* __restrict__ slots, long long n,
-                          const V4<T>* __restrict__ posm, const V4<T>* __restrict__ vel,
-                          const int* __restrict__ id, V4<T>* __restrict__ posm_o,
-                          V4<T>* __restrict__ vel_o, int* __restrict__ id_o) {
-  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t s = slots[i];
-  posm_o[i] = posm[s];
-  vel_o[i] = vel[s];
-  id_o[i] = id[s];
-}
-
-// cell_start[c] = first sorted slot whose cell code is >= c (lower bound), c in [0, ncells]
-__global__ void k_cell_start(const uint64_t* __restrict__ keys, long long n, int idbits,
-                             long long ncells, int* __restrict__ cell_start) {
-  long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (c > ncells) return;
-  const uint64_t target = (uint64_t)c << idbits;
-  long long lo = 0, hi = n;
-  while (lo < hi) {
-    long long mid = (lo + hi) >> 1;
-    if (keys[mid] < target)
-      lo = mid + 1;
-    else
-      hi = mid;
-  }
-  cell_start[c] = (int)lo;
-}
-
-// bounding box of every globally aligned tile of kPPTile consecutive (sorted) particles: one warp per
-// tile, 8 coalesced 128-bit loads per lane.  Consumed by the short-range kernel to skip source tiles
-// that cannot reach a target group.
-template <typename T>
-__global__ void __launch_bounds__(256)
-k_tile_aabb(const V4<T>* __restrict__ posm, long long n, V4<T>* __restrict__ aabb) {
-  const long long tile = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const long long b = tile * kPPTile;
-  if (b >= n) return;
-  T lx = 1e30, ly = 1e30, lz = 1e30, hx = -1e30, hy = -1e30, hz = -1e30;
-  for (int k = lane; k < kPPTile && b + k < n; k += 32) {
-    const V4<T> p = posm[b + k];
-    lx = min(lx, p.x), ly = min(ly, p.y), lz = min(lz, p.z);
-    hx = max(hx, p.x), hy = max(hy, p.y), hz = max(hz, p.z);
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    lx = min(lx, __shfl_xor_sync(0xffffffffu, lx, o)), ly = min(ly, __shfl_xor_sync(0xffffffffu, ly, o));
-    lz = min(lz, __shfl_xor_sync(0xffffffffu, lz, o)), hx = max(hx, __shfl_xor_sync(0xffffffffu, hx, o));
-    hy = max(hy, __shfl_xor_sync(0xffffffffu, hy, o)), hz = max(hz, __shfl_xor_sync(0xffffffffu, hz, o));
-  }
-  if (lane == 0) {
-    aabb[2 * tile] = V4<T>{lx, ly, lz, 0};
-    aabb[2 * tile + 1] = V4<T>{hx, hy, hz, 0};
-  }
-}
-
 template <typename T>
 int bin_sort(p3m_ctx* c) {
   if (!c->have_particles) return fail(P3M_ESTATE, "p3m_bin_sort: no particles set");
   State<T>& s = Sel<T>::st(c);
   Geom<T>& g = Sel<T>::g(c);
+  if (c->nranks > 1) P3M_TRY(dist_migrate<T>(c, true));  // particles that left this rank's z-slab
   const long long n = c->n;
+  const long long nid = c->nranks > 1 ? c->n_global : n;  // ids are global
   int idbits = 1;
-  while ((1LL << idbits) < n) ++idbits;
+  while ((1LL << idbits) < nid) ++idbits;
   g.idbits = idbits;
   g.sbits = 0;
   if (g.p3m) {
@@ -280,6 +287,7 @@ int bin_sort(p3m_ctx* c) {
   P3M_LAUNCH_CHECK(c);
   phase_end(c, PH_BINSORT);
   c->sorted = true;
+  if (c->nranks > 1) P3M_TRY(dist_ghosts<T>(c));  // boundary-layer particles of the neighbour slabs
   return 0;
 }
 
@@ -313,20 +321,24 @@ __global__ void k_cells_out(const V4<T>* __restrict__ posm, const int* __restric
 template <typename T>
 int get_cells(p3m_ctx* c, int32_t* mesh_cell, int32_t* chain_cell, int32_t* order) {
   State<T>& s = Sel<T>::st(c);
-  const long long n = c->n;
-  if (n == 0) return 0;
+  const long long n = c->n;                                      // local particles
+  const long long ng = c->nranks > 1 ? c->n_global : n;          // id-indexed outputs
+  if (ng == 0) return 0;
   int* stage = nullptr;
-  P3M_CUDA(cudaMallocAsync((void**)&stage, sizeof(int) * 3 * (size_t)n, c->stream));
-  k_cells_out<T><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
-      s.posm, s.id, n, Sel<T>::g(c), mesh_cell ? stage : nullptr, chain_cell ? stage + n : nullptr,
-      order ? stage + 2 * n : nullptr);
-  P3M_LAUNCH_CHECK(c);
+  P3M_CUDA(cudaMallocAsync((void**)&stage, sizeof(int) * (2 * (size_t)ng + (size_t)n + 1), c->stream));
+  if (c->nranks > 1) P3M_CUDA(cudaMemsetAsync(stage, 0xff, sizeof(int) * 2 * (size_t)ng, c->stream));
+  if (n > 0) {
+    k_cells_out<T><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+        s.posm, s.id, n, Sel<T>::g(c), mesh_cell ? stage : nullptr, chain_cell ? stage + ng : nullptr,
+        order ? stage + 2 * ng : nullptr);
+    P3M_LAUNCH_CHECK(c);
+  }
   if (mesh_cell)
-    P3M_CUDA(cudaMemcpyAsync(mesh_cell, stage, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+    P3M_CUDA(cudaMemcpyAsync(mesh_cell, stage, sizeof(int) * ng, cudaMemcpyDeviceToHost, c->stream));
   if (chain_cell)
-    P3M_CUDA(cudaMemcpyAsync(chain_cell, stage + n, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
-  if (order)
-    P3M_CUDA(cudaMemcpyAsync(order, stage + 2 * n, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+    P3M_CUDA(cudaMemcpyAsync(chain_cell, stage + ng, sizeof(int) * ng, cudaMemcpyDeviceToHost, c->stream));
+  if (order && n > 0)
+    P3M_CUDA(cudaMemcpyAsync(order, stage + 2 * ng, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
   P3M_CUDA(cudaFreeAsync(stage, c->stream));
   P3M_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
@@ -367,7 +379,7 @@ void free_state(p3m_ctx* c) {
   State<T>& s = Sel<T>::st(c);
   void* ptrs[] = {s.posm,   s.posm_alt,  s.vel,      s.vel_alt,  s.acc,        s.acc_sr,  s.id,
                   s.id_alt, s.keys,      s.keys_alt, s.slots,    s.slots_alt,  s.cub_tmp, s.cell_start,
-                  s.density, s.potential, s.spectrum, s.green,    s.field,      s.sr_table, s.pp_items, s.aabb,
+                  s.density, s.potential, s.spectrum, s.green,    s.field,      s.sr_table, s.pp_items, s.aabb, s.gposm, s.gposm_alt, s.gid, s.gid_alt, s.gcell_start, s.gaabb,
                   s.pp_counters, s.pair_counts, s.flags, s.diag};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -381,6 +393,8 @@ void free_state(p3m_ctx* c) {
 #define INST(T)                                                                                  \
   template int alloc_particles<T>(p3m_ctx*, long long);                                          \
   template int upload_particles<T>(p3m_ctx*, const float*, const float*, const float*, long long, int); \
+  template int upload_particles_ids<T>(p3m_ctx*, const float*, const float*, const float*, const int32_t*, long long, int); \
+  template int download_local<T>(p3m_ctx*, int32_t*, float*, float*, float*, int); \
   template int download_particles<T, float>(p3m_ctx*, float*, float*, float*, int);              \
   template int download_particles<T, double>(p3m_ctx*, double*, double*, double*, int);          \
   template int bin_sort<T>(p3m_ctx*);                                                            \

@@ -194,6 +194,7 @@ int p3m_create(const p3m_params* prm, p3m_ctx** out) {
     c->mass_factor64 = dDT * dDT * 4 * dpi * dG / (dH * dH * dH);
   }
   int r = c->f64 ? create_typed<double>(c) : create_typed<float>(c);
+  if (r == 0) r = dist_init(c, nullptr, 0, 1);  // single rank: owns every layer
   if (r != 0) {
     p3m_destroy(c);
     return r;
@@ -202,10 +203,76 @@ int p3m_create(const p3m_params* prm, p3m_ctx** out) {
   return 0;
 }
 
+int p3m_slab_cuts(const p3m_params* prm, int nranks, int32_t cuts[9], int32_t* layers_out) {
+  if (!prm || !cuts || nranks < 1 || nranks > 8) return fail(P3M_EINVAL, "p3m_slab_cuts: bad argument");
+  p3m_ctx c;
+  c.prm = *prm;
+  c.f64 = false;
+  c.rank = 0, c.nranks = nranks;
+  int r = setup_geometry<float>(&c);
+  if (r != 0) return r;
+  dist_set_cuts(&c);
+  for (int i = 0; i < 9; ++i) cuts[i] = c.g32.cut[i];
+  if (layers_out) *layers_out = c.g32.cut[nranks];
+  if (c.g32.cut[nranks] < nranks) return fail(P3M_EINVAL, "only %d binning layers along z for %d ranks", c.g32.cut[nranks], nranks);
+  return 0;
+}
+
+int p3m_comm_unique_id(void* out) {
+  if (!out) return fail(P3M_EINVAL, "null output");
+  return comm_unique_id(out);
+}
+
+int p3m_create_dist(const p3m_params* prm, const void* uid, int rank, int nranks, p3m_ctx** out) {
+  if (!uid && nranks > 1) return fail(P3M_EINVAL, "p3m_create_dist: null unique id");
+  p3m_ctx* c = nullptr;
+  int r = p3m_create(prm, &c);
+  if (r != 0) return r;
+  r = dist_init(c, uid, rank, nranks);
+  if (r != 0) {
+    p3m_destroy(c);
+    return r;
+  }
+  *out = c;
+  return 0;
+}
+
+int p3m_get_local(p3m_ctx* c, int32_t* ids, float* pos, float* vel, float* acc, int units) {
+  if (!c) return fail(P3M_EINVAL, "null context");
+  P3M_CUDA(cudaSetDevice(c->device));
+  if (!c->have_particles) return fail(P3M_ESTATE, "no particles set");
+  return P3M_DISPATCH(c, download_local, ids, pos, vel, acc, units);
+}
+
+int p3m_set_particles_ids(p3m_ctx* c, const float* pos, const float* vel, const float* mass, const int32_t* ids,
+                          int64_t n, int units) {
+  if (!c) return fail(P3M_EINVAL, "null context");
+  P3M_CUDA(cudaSetDevice(c->device));
+  if (n < 0 || (n > 0 && (!pos || !mass || !ids))) return fail(P3M_EINVAL, "p3m_set_particles_ids: bad argument");
+  int r = P3M_DISPATCH(c, upload_particles_ids, pos, vel, mass, ids, (long long)n, units);
+  if (r == 0) {
+    int* flags = c->f64 ? c->s64.flags : c->s32.flags;
+    P3M_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 4, c->stream));
+  }
+  return r;
+}
+
+int64_t p3m_num_global(const p3m_ctx* c) { return c ? (c->nranks > 1 ? c->n_global : c->n) : 0; }
+
+int p3m_rank_info(p3m_ctx* c, int64_t out[5]) {
+  if (!c || !out) return fail(P3M_EINVAL, "null argument");
+  out[0] = c->rank, out[1] = c->nranks;
+  out[2] = c->f64 ? c->g64.cut[c->rank] : c->g32.cut[c->rank];
+  out[3] = c->f64 ? c->g64.cut[c->rank + 1 > 8 ? 8 : c->rank + 1] : c->g32.cut[c->rank + 1 > 8 ? 8 : c->rank + 1];
+  out[4] = c->f64 ? c->s64.n_ghost : c->s32.n_ghost;
+  return 0;
+}
+
 int p3m_destroy(p3m_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  dist_destroy(c);
   free_state<float>(c);
   free_state<double>(c);
   for (int i = 0; i < P3M_NPHASE; ++i) {

@@ -68,7 +68,21 @@ struct Geom {
   T H, DT;
   T boxx, boxy, boxz;  // effective box, original units (escape check)
   int unit_roundtrip;
+  // z-slab decomposition of the particles over nranks GPUs (dist.cu); nranks == 1: everything local.
+  // Binning-cell layers [cut[r], cut[r+1]) along z belong to rank r (the last rank also takes every
+  // layer above cut[nranks]); lay0/lay1 = this rank's own range.
+  int nranks, rank;
+  int cut[9];
+  int lay0, lay1;
 };
+
+// owner rank of a binning-cell layer
+template <typename T>
+__host__ __device__ inline int layer_owner(const Geom<T>& g, int cz) {
+  int r = 0;
+  for (int k = 1; k < g.nranks; ++k) r += (cz >= g.cut[k]) ? 1 : 0;
+  return r;
+}
 
 template <typename T>
 struct SRParams {

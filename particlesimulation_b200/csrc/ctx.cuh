@@ -29,6 +29,12 @@ struct State {
   size_t cub_tmp_bytes = 0;
   int* cell_start = nullptr;  // (1 << 3*mbits) + 1 entries
   V4<T>* aabb = nullptr;      // 2 per kPPTile-particle tile: (lo.xyz, -), (hi.xyz, -)
+  // ghost particles of the two neighbouring z-slabs (dist.cu), sorted by the same key
+  V4<T>*gposm = nullptr, *gposm_alt = nullptr;
+  int *gid = nullptr, *gid_alt = nullptr;
+  int* gcell_start = nullptr;
+  V4<T>* gaabb = nullptr;
+  long long n_ghost = 0, ghost_cap = 0;
   // meshes
   T* density = nullptr;    // M
   T* potential = nullptr;  // M
@@ -72,6 +78,12 @@ struct p3m_ctx {
   p3m::PhaseTimer timer;
   bool timing = false;
   int count_pairs = 0;
+  // multi-GPU (z-slabs of particles, NCCL): dist.cu
+  void* nccl_comm = nullptr;  // ncclComm_t
+  int rank = 0, nranks = 1;
+  long long n_global = 0;
+  int* dist_counts = nullptr;       // device: nranks + 1 segment starts, then nranks*nranks counts, then 4 ghost counts * nranks
+  int* dist_counts_host = nullptr;  // pinned mirror
 };
 
 namespace p3m {
@@ -132,6 +144,17 @@ template <typename T> int get_cells(p3m_ctx* c, int32_t* mesh_cell, int32_t* cha
 template <typename T> int get_acc_parts(p3m_ctx* c, double* acc_pm, double* acc_sr);
 template <typename T> int add_acceleration(p3m_ctx* c, const float* a, int units);
 int fft3d_c2c(int nz, int ny, int nx, const float* in, float* out, int inverse);
+// dist.cu
+int comm_unique_id(void* out128);
+void dist_set_cuts(p3m_ctx* c);
+int dist_init(p3m_ctx* c, const void* unique_id, int rank, int nranks);
+void dist_destroy(p3m_ctx* c);
+template <typename T> int dist_migrate(p3m_ctx* c, bool exchange);
+template <typename T> int dist_ghosts(p3m_ctx* c);
+template <typename T> int dist_allreduce_density(p3m_ctx* c);
+int dist_allreduce(p3m_ctx* c, void* buf, size_t count, int kind /*0 int max, 1 double sum*/);
+template <typename T> int upload_particles_ids(p3m_ctx* c, const float* pos, const float* vel, const float* mass, const int32_t* ids, long long n, int units);
+template <typename T> int download_local(p3m_ctx* c, int32_t* ids, float* pos, float* vel, float* acc, int units);
 template <typename T, typename O> int get_mesh(p3m_ctx* c, const T* dev, O* out, long long count);
 template <typename T, typename I> int set_mesh(p3m_ctx* c, T* dev, const I* in, long long count);
 

@@ -221,6 +221,7 @@ int deposit(p3m_ctx* c) {
       r = launch_deposit<T, 1>(c);
   }
   phase_end(c, PH_DEPOSIT);
+  if (r == 0 && c->nranks > 1) r = dist_allreduce_density<T>(c);  // sum the slabs' contributions
   c->have_density = (r == 0);
   return r;
 }

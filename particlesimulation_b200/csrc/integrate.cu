@@ -78,11 +78,14 @@ template <typename T>
 int drift(p3m_ctx* c) {
   if (!c->have_particles) return fail(P3M_ESTATE, "p3m_drift: no particles set");
   State<T>& s = Sel<T>::st(c);
-  if (c->n == 0) return 0;
+  if (c->n == 0 && c->nranks == 1) return 0;
   phase_begin(c, PH_INTEGRATE);
-  k_drift<T><<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(s.posm, s.vel, c->n, Sel<T>::g(c),
-                                                                   s.flags, s.flags + 3);
-  P3M_LAUNCH_CHECK(c);
+  if (c->n > 0) {
+    k_drift<T><<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(s.posm, s.vel, c->n, Sel<T>::g(c),
+                                                                     s.flags, s.flags + 3);
+    P3M_LAUNCH_CHECK(c);
+  }
+  P3M_TRY(dist_allreduce(c, s.flags + 3, 1, 0));  // every rank must take the same decision
   k_publish_escape<<<1, 1, 0, c->stream>>>(s.flags);
   P3M_LAUNCH_CHECK(c);
   phase_end(c, PH_INTEGRATE);
@@ -159,9 +162,10 @@ k_diag_particles(const V4<T>* __restrict__ posm, const V4<T>* __restrict__ vel,
 // out[11] += sum rho * phi (code units)
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_diag_mesh(const T* __restrict__ rho, const T* __restrict__ phi, long long M, double* __restrict__ out) {
+k_diag_mesh(const T* __restrict__ rho, const T* __restrict__ phi, long long first, long long M,
+            double* __restrict__ out) {
   double v[1] = {0};
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M;
+  for (long long i = first + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M;
        i += (long long)gridDim.x * blockDim.x)
     v[0] += (double)rho[i] * (double)phi[i];
   block_accumulate<1>(v, out + 11);
@@ -180,9 +184,13 @@ int diagnostics(p3m_ctx* c, double* out) {
     P3M_LAUNCH_CHECK(c);
   }
   if (c->have_density && c->have_potential) {
-    k_diag_mesh<T><<<blocks, 256, 0, c->stream>>>(s.density, s.potential, g.M, s.diag);
+    // the mesh is replicated on every rank: each sums its share of the cells
+    const long long share = (g.M + c->nranks - 1) / c->nranks;
+    const long long first = share * c->rank, last = first + share < g.M ? first + share : g.M;
+    k_diag_mesh<T><<<blocks, 256, 0, c->stream>>>(s.density, s.potential, first, last, s.diag);
     P3M_LAUNCH_CHECK(c);
   }
+  P3M_TRY(dist_allreduce(c, s.diag, 16, 1));
   double h[16];
   P3M_CUDA(cudaMemcpyAsync(h, s.diag, sizeof(double) * 16, cudaMemcpyDeviceToHost, c->stream));
   P3M_CUDA(cudaStreamSynchronize(c->stream));
@@ -210,13 +218,17 @@ __global__ void k_acc_parts(const V4<T>* __restrict__ acc, const V4<T>* __restri
 template <typename T>
 int get_acc_parts(p3m_ctx* c, double* acc_pm, double* acc_sr) {
   State<T>& s = Sel<T>::st(c);
-  const long long n = c->n;
+  const long long nl = c->n;
+  const long long n = c->nranks > 1 ? c->n_global : nl;  // id-indexed outputs
   if (n == 0) return 0;
   double* stage = nullptr;
   P3M_CUDA(cudaMallocAsync((void**)&stage, sizeof(double) * 6 * (size_t)n, c->stream));
-  k_acc_parts<T><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
-      s.acc, s.acc_sr, s.id, n, acc_pm ? stage : nullptr, acc_sr ? stage + 3 * n : nullptr);
-  P3M_LAUNCH_CHECK(c);
+  if (c->nranks > 1) P3M_CUDA(cudaMemsetAsync(stage, 0, sizeof(double) * 6 * (size_t)n, c->stream));
+  if (nl > 0) {
+    k_acc_parts<T><<<(unsigned)((nl + 255) / 256), 256, 0, c->stream>>>(
+        s.acc, s.acc_sr, s.id, nl, acc_pm ? stage : nullptr, acc_sr ? stage + 3 * n : nullptr);
+    P3M_LAUNCH_CHECK(c);
+  }
   if (acc_pm) P3M_CUDA(cudaMemcpyAsync(acc_pm, stage, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
   if (acc_sr) P3M_CUDA(cudaMemcpyAsync(acc_sr, stage + 3 * n, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
   P3M_CUDA(cudaFreeAsync(stage, c->stream));
@@ -233,6 +245,7 @@ int escaped_now(p3m_ctx* c, int* escaped) {
                                                                        s.pp_counters + 4);
     P3M_LAUNCH_CHECK(c);
   }
+  P3M_TRY(dist_allreduce(c, s.pp_counters + 4, 1, 0));
   P3M_CUDA(cudaMemcpyAsync(escaped, s.pp_counters + 4, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   P3M_CUDA(cudaStreamSynchronize(c->stream));
   return 0;

@@ -154,7 +154,9 @@ __global__ void k_pp_items(const int* __restrict__ cell_start, Geom<T> g, int* _
 template <typename T, bool TABLE, bool COUNT>
 __global__ void __launch_bounds__(128)
 k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
-           const V4<T>* __restrict__ aabb, const int* __restrict__ items,
+           const V4<T>* __restrict__ aabb, const V4<T>* __restrict__ gposm,
+           const int* __restrict__ gcell_start, const V4<T>* __restrict__ gaabb,
+           const int* __restrict__ items,
            const unsigned* __restrict__ order, int* __restrict__ counters, Geom<T> g, SRParams<T> sp,
            const T* __restrict__ g_tab, V4<T>* __restrict__ acc, V4<T>* __restrict__ acc_sr,
            unsigned long long* __restrict__ pair_counts) {
@@ -214,11 +216,16 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
           const int x = cx + dx, y = cy + dy, z = cz + dz;
           if (x < 0 || y < 0 || z < 0 || x >= g.mx || y >= g.my || z >= g.mz) continue;
           const uint32_t qn = morton3((uint32_t)x, (uint32_t)y, (uint32_t)z);
-          const int s = cell_start[qn], e = cell_start[qn + 1];
+          // multi-GPU: cells of a foreign z-layer are served from the ghost copy of the neighbour slab
+          const bool own = g.nranks == 1 || layer_owner(g, z) == g.rank;
+          const V4<T>* __restrict__ spos = own ? posm : gposm;
+          const int* __restrict__ scs = own ? cell_start : gcell_start;
+          const V4<T>* __restrict__ sbb = own ? aabb : gaabb;
+          const int s = scs[qn], e = scs[qn + 1];
           if (s >= e) continue;
           for (int tile = s / kPPTile; tile <= (e - 1) / kPPTile; ++tile) {
             // exact culling: box-box distance beyond the cutoff => no pair of this tile is in range
-            const V4<T> blo = aabb[2 * tile], bhi = aabb[2 * tile + 1];
+            const V4<T> blo = sbb[2 * tile], bhi = sbb[2 * tile + 1];
             const T gx = max(T(0), max(blo.x - thi[0], tlo[0] - bhi.x));
             const T gy = max(T(0), max(blo.y - thi[1], tlo[1] - bhi.y));
             const T gz = max(T(0), max(blo.z - thi[2], tlo[2] - bhi.z));
@@ -226,8 +233,8 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
             const int jb = max(s, tile * kPPTile), je = min(e, (tile + 1) * kPPTile);
             __syncthreads();
             const int j0 = jb + tid, j1 = jb + 128 + tid;
-            if (j0 < je) s_src[tid] = posm[j0];
-            if (j1 < je) s_src[tid + 128] = posm[j1];
+            if (j0 < je) s_src[tid] = spos[j0];
+            if (j1 < je) s_src[tid + 128] = spos[j1];
             __syncthreads();
             const int cnt = je - jb;
             if (COUNT) checked += (unsigned long long)cnt * ((v0 ? 1 : 0) + (v1 ? 1 : 0));
@@ -264,7 +271,7 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
 template <typename T, bool TABLE, bool COUNT>
 __global__ void __launch_bounds__(128)
 k_pp_sparse(const V4<T>* __restrict__ posm, long long n, const int* __restrict__ cell_start,
-            Geom<T> g, SRParams<T> sp, const T* __restrict__ g_tab, V4<T>* __restrict__ acc,
+            const V4<T>* __restrict__ gposm, const int* __restrict__ gcell_start, Geom<T> g, SRParams<T> sp, const T* __restrict__ g_tab, V4<T>* __restrict__ acc,
             V4<T>* __restrict__ acc_sr, unsigned long long* __restrict__ pair_counts) {
   __shared__ V2<T> s_tab[kSRTable];
   __shared__ unsigned s_tb;
@@ -289,10 +296,13 @@ k_pp_sparse(const V4<T>* __restrict__ posm, long long n, const int* __restrict__
         const int x = cx + dx, y = cy + dy, z = cz + dz;
         if (x < 0 || y < 0 || z < 0 || x >= g.mx || y >= g.my || z >= g.mz) continue;
         const uint32_t qn = morton3((uint32_t)x, (uint32_t)y, (uint32_t)z);
-        const int s = cell_start[qn], e = cell_start[qn + 1];
+        const bool own = g.nranks == 1 || layer_owner(g, z) == g.rank;
+        const V4<T>* __restrict__ spos = own ? posm : gposm;
+        const int* __restrict__ scs = own ? cell_start : gcell_start;
+        const int s = scs[qn], e = scs[qn + 1];
         if (COUNT) checked += (unsigned long long)(e - s);
         for (int j = s; j < e; ++j) {
-          const V4<T> sj = posm[j];
+          const V4<T> sj = spos[j];
           pair_acc<T, TABLE, COUNT>(p.x - sj.x, p.y - sj.y, p.z - sj.z, sj.w, sp, tref, ax, ay, az,
                                     n_in);
         }
@@ -406,11 +416,11 @@ static int run_pp(p3m_ctx* c) {
                                                      (int)max_items, 0, 32, c->stream));
   c->launches += 5;
   k_pp_tiled<T, TABLE, COUNT><<<c->num_sms * 8, 128, 0, c->stream>>>(
-      s.posm, s.cell_start, s.aabb, s.pp_items, order, s.pp_counters, g, sp, s.sr_table, s.acc,
-      s.acc_sr, s.pair_counts);
+      s.posm, s.cell_start, s.aabb, s.gposm, s.gcell_start, s.gaabb, s.pp_items, order, s.pp_counters, g, sp,
+      s.sr_table, s.acc, s.acc_sr, s.pair_counts);
   P3M_LAUNCH_CHECK(c);
   k_pp_sparse<T, TABLE, COUNT><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(
-      s.posm, n, s.cell_start, g, sp, s.sr_table, s.acc, s.acc_sr, s.pair_counts);
+      s.posm, n, s.cell_start, s.gposm, s.gcell_start, g, sp, s.sr_table, s.acc, s.acc_sr, s.pair_counts);
   P3M_LAUNCH_CHECK(c);
   return 0;
 }

@@ -1,0 +1,93 @@
+// sort_kernels.cuh -- kernels shared by the local cell sort (binsort.cu) and the ghost-particle sort
+// of the multi-GPU path (dist.cu).
+#pragma once
+
+#include "ctx.cuh"
+
+namespace p3m {
+
+// ---- A0: sort keys ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_keys(const V4<T>* __restrict__ posm, const int* __restrict__ id, long long n,
+                       Geom<T> g, uint64_t* __restrict__ keys, uint32_t* __restrict__ slots,
+                       int* __restrict__ flags) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  V4<T> p = posm[i];
+  int cx, cy, cz;
+  bool inside;
+  bin_cell(g, p.x, p.y, p.z, cx, cy, cz, inside);
+  if (!inside) flags[1] = 1;
+  uint64_t m = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+  if (g.sbits) {
+    // position inside the chaining cell in units of 1/2^sbits of the cell: x/HC - cx is exact in
+    // floating point (cx is the truncation of the same quotient), so the sub-cell is reproducible
+    const int S = 1 << g.sbits;
+    int sx = (int)((p.x / g.hcx - (T)cx) * (T)S), sy = (int)((p.y / g.hcy - (T)cy) * (T)S),
+        sz = (int)((p.z / g.hcz - (T)cz) * (T)S);
+    sx = min(max(sx, 0), S - 1), sy = min(max(sy, 0), S - 1), sz = min(max(sz, 0), S - 1);
+    m = (m << (3 * g.sbits)) | morton3((uint32_t)sx, (uint32_t)sy, (uint32_t)sz);
+  }
+  keys[i] = (m << g.idbits) | (uint64_t)(uint32_t)id[i];
+  slots[i] = (uint32_t)i;
+}
+
+template <typename T>
+__global__ void k_permute(const uint32_t* __restrict__ slots, long long n,
+                          const V4<T>* __restrict__ posm, const V4<T>* __restrict__ vel,
+                          const int* __restrict__ id, V4<T>* __restrict__ posm_o,
+                          V4<T>* __restrict__ vel_o, int* __restrict__ id_o) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s = slots[i];
+  posm_o[i] = posm[s];
+  vel_o[i] = vel[s];
+  id_o[i] = id[s];
+}
+
+// cell_start[c] = first sorted slot whose cell code is >= c (lower bound), c in [0, ncells]
+static __global__ void k_cell_start(const uint64_t* __restrict__ keys, long long n, int idbits,
+                             long long ncells, int* __restrict__ cell_start) {
+  long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (c > ncells) return;
+  const uint64_t target = (uint64_t)c << idbits;
+  long long lo = 0, hi = n;
+  while (lo < hi) {
+    long long mid = (lo + hi) >> 1;
+    if (keys[mid] < target)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  cell_start[c] = (int)lo;
+}
+
+// bounding box of every globally aligned tile of kPPTile consecutive (sorted) particles: one warp per
+// tile, 8 coalesced 128-bit loads per lane.  Consumed by the short-range kernel to skip source tiles
+// that cannot reach a target group.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_tile_aabb(const V4<T>* __restrict__ posm, long long n, V4<T>* __restrict__ aabb) {
+  const long long tile = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long b = tile * kPPTile;
+  if (b >= n) return;
+  T lx = 1e30, ly = 1e30, lz = 1e30, hx = -1e30, hy = -1e30, hz = -1e30;
+  for (int k = lane; k < kPPTile && b + k < n; k += 32) {
+    const V4<T> p = posm[b + k];
+    lx = min(lx, p.x), ly = min(ly, p.y), lz = min(lz, p.z);
+    hx = max(hx, p.x), hy = max(hy, p.y), hz = max(hz, p.z);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lx = min(lx, __shfl_xor_sync(0xffffffffu, lx, o)), ly = min(ly, __shfl_xor_sync(0xffffffffu, ly, o));
+    lz = min(lz, __shfl_xor_sync(0xffffffffu, lz, o)), hx = max(hx, __shfl_xor_sync(0xffffffffu, hx, o));
+    hy = max(hy, __shfl_xor_sync(0xffffffffu, hy, o)), hz = max(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+  }
+  if (lane == 0) {
+    aabb[2 * tile] = V4<T>{lx, ly, lz, 0};
+    aabb[2 * tile + 1] = V4<T>{hx, hy, hz, 0};
+  }
+}
+
+
+}  // namespace p3m
