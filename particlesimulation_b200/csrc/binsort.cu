@@ -38,7 +38,7 @@ int alloc_particles(p3m_ctx* c, long long n) {
   P3M_TRY(dev_alloc(&s.keys_alt, cap));
   P3M_TRY(dev_alloc(&s.slots, cap));
   P3M_TRY(dev_alloc(&s.slots_alt, cap));
-  P3M_TRY(dev_alloc(&s.aabb, 2 * (cap / kPPTile + 2)));
+  P3M_TRY(dev_alloc(&s.aabb, 2 * (cap / kPPSub + 8)));
   P3M_TRY(dev_alloc(&s.pp_items, 2 * (cap / kPPTargets + ((size_t)1 << (3 * Sel<T>::g(c).mbits)) + 16)));
   size_t tmp = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tmp, s.keys, s.keys_alt, s.slots, s.slots_alt, (int)cap, 0,
@@ -277,7 +277,7 @@ int bin_sort(p3m_ctx* c) {
     std::swap(s.vel, s.vel_alt);
     std::swap(s.id, s.id_alt);
     if (g.p3m) {
-      const long long tiles = (n + kPPTile - 1) / kPPTile;
+      const long long tiles = (n + kPPSub - 1) / kPPSub;
       k_tile_aabb<T><<<(unsigned)((tiles * 32 + 255) / 256), 256, 0, c->stream>>>(s.posm, n, s.aabb);
       P3M_LAUNCH_CHECK(c);
     }

@@ -282,7 +282,7 @@ int dist_ghosts(p3m_ctx* c) {
     P3M_TRY(dev_realloc(&s.gid, c->cap));
     P3M_TRY(dev_realloc(&s.gid_alt, c->cap));
     P3M_TRY(dev_realloc(&s.gcell_start, ncells + 2));
-    P3M_TRY(dev_realloc(&s.gaabb, 2 * (c->cap / kPPTile + 2)));
+    P3M_TRY(dev_realloc(&s.gaabb, 2 * (c->cap / kPPSub + 8)));
     s.ghost_cap = c->cap;
   }
   phase_begin(c, PH_COMM);
@@ -343,7 +343,7 @@ int dist_ghosts(p3m_ctx* c) {
     P3M_LAUNCH_CHECK(c);
     std::swap(s.gposm, s.gposm_alt);
     std::swap(s.gid, s.gid_alt);
-    const long long tiles = (ng + kPPTile - 1) / kPPTile;
+    const long long tiles = (ng + kPPSub - 1) / kPPSub;
     k_tile_aabb<T><<<(unsigned)((tiles * 32 + 255) / 256), 256, 0, c->stream>>>(s.gposm, ng, s.gaabb);
     P3M_LAUNCH_CHECK(c);
   }

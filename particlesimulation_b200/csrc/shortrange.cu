@@ -152,7 +152,7 @@ __global__ void k_pp_items(const int* __restrict__ cell_start, Geom<T> g, int* _
 }
 
 template <typename T, bool TABLE, bool COUNT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
            const V4<T>* __restrict__ aabb, const V4<T>* __restrict__ gposm,
            const int* __restrict__ gcell_start, const V4<T>* __restrict__ gaabb,
@@ -183,10 +183,12 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
     const uint32_t q = (uint32_t)items[2 * item];
     const int t0 = items[2 * item + 1];
     const int tend = min(cell_start[q + 1], t0 + kPPTargets);
-    const int i0 = t0 + tid, i1 = t0 + 128 + tid;
+    // warp w owns targets [t0 + 64 w, t0 + 64 w + 64): lane l holds 64 w + l and 64 w + 32 + l
+    const int i0 = t0 + 64 * wid + lane, i1 = i0 + 32;
     const bool v0 = i0 < tend, v1 = i1 < tend;
     const V4<T> p0 = posm[v0 ? i0 : t0], p1 = posm[v1 ? i1 : t0];
-    // bounding box of the target group (code units)
+    // bounding boxes (code units): of this warp's 64 targets (registers) and of the whole group (smem)
+    T wlo[3], whi[3];
     {
       T lx = min(p0.x, p1.x), ly = min(p0.y, p1.y), lz = min(p0.z, p1.z);
       T hx = max(p0.x, p1.x), hy = max(p0.y, p1.y), hz = max(p0.z, p1.z);
@@ -195,6 +197,7 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
         lz = min(lz, __shfl_xor_sync(0xffffffffu, lz, o)), hx = max(hx, __shfl_xor_sync(0xffffffffu, hx, o));
         hy = max(hy, __shfl_xor_sync(0xffffffffu, hy, o)), hz = max(hz, __shfl_xor_sync(0xffffffffu, hz, o));
       }
+      wlo[0] = lx, wlo[1] = ly, wlo[2] = lz, whi[0] = hx, whi[1] = hy, whi[2] = hz;
       if (lane == 0) {
         s_box[wid][0] = lx, s_box[wid][1] = ly, s_box[wid][2] = lz;
         s_box[wid][3] = hx, s_box[wid][4] = hy, s_box[wid][5] = hz;
@@ -224,29 +227,46 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
           const int s = scs[qn], e = scs[qn + 1];
           if (s >= e) continue;
           for (int tile = s / kPPTile; tile <= (e - 1) / kPPTile; ++tile) {
-            // exact culling: box-box distance beyond the cutoff => no pair of this tile is in range
-            const V4<T> blo = sbb[2 * tile], bhi = sbb[2 * tile + 1];
-            const T gx = max(T(0), max(blo.x - thi[0], tlo[0] - bhi.x));
-            const T gy = max(T(0), max(blo.y - thi[1], tlo[1] - bhi.y));
-            const T gz = max(T(0), max(blo.z - thi[2], tlo[2] - bhi.z));
-            if (gx * gx + gy * gy + gz * gz > cut2) continue;  // CTA-uniform
+            // exact culling on the 4 bounding boxes (64 particles each) of this tile: lanes 0..3 test one
+            // box each against the group's box (all warps agree -> CTA-uniform skip of the staging) and
+            // against this warp's own box (warp-uniform skip of the 64-source inner loop)
+            T dg = T(1e30), dw = T(1e30);
+            const int sub = tile * (kPPTile / kPPSub) + lane;
+            if (lane < kPPTile / kPPSub && sub * kPPSub < e && (sub + 1) * kPPSub > s) {
+              const V4<T> blo = sbb[2 * sub], bhi = sbb[2 * sub + 1];
+              T gx = max(T(0), max(blo.x - thi[0], tlo[0] - bhi.x));
+              T gy = max(T(0), max(blo.y - thi[1], tlo[1] - bhi.y));
+              T gz = max(T(0), max(blo.z - thi[2], tlo[2] - bhi.z));
+              dg = gx * gx + gy * gy + gz * gz;
+              gx = max(T(0), max(blo.x - whi[0], wlo[0] - bhi.x));
+              gy = max(T(0), max(blo.y - whi[1], wlo[1] - bhi.y));
+              gz = max(T(0), max(blo.z - whi[2], wlo[2] - bhi.z));
+              dw = gx * gx + gy * gy + gz * gz;
+            }
+            if (__ballot_sync(0xffffffffu, dg <= cut2) == 0u) continue;  // CTA-uniform
+            const unsigned near = __ballot_sync(0xffffffffu, dw <= cut2);
             const int jb = max(s, tile * kPPTile), je = min(e, (tile + 1) * kPPTile);
             __syncthreads();
             const int j0 = jb + tid, j1 = jb + 128 + tid;
             if (j0 < je) s_src[tid] = spos[j0];
             if (j1 < je) s_src[tid + 128] = spos[j1];
             __syncthreads();
-            const int cnt = je - jb;
-            if (COUNT) checked += (unsigned long long)cnt * ((v0 ? 1 : 0) + (v1 ? 1 : 0));
+#pragma unroll 1
+            for (int k = 0; k < kPPTile / kPPSub; ++k) {
+              if (!((near >> k) & 1u)) continue;  // warp-uniform
+              const int kb = max(jb, (tile * (kPPTile / kPPSub) + k) * kPPSub) - jb;
+              const int ke = min(je, (tile * (kPPTile / kPPSub) + k + 1) * kPPSub) - jb;
+              if (COUNT) checked += (unsigned long long)max(ke - kb, 0) * ((v0 ? 1 : 0) + (v1 ? 1 : 0));
 #pragma unroll 4
-            for (int j = 0; j < cnt; ++j) {
-              const V4<T> sj = s_src[j];
-              unsigned c0 = 0, c1 = 0;
-              pair_acc<T, TABLE, COUNT>(p0.x - sj.x, p0.y - sj.y, p0.z - sj.z, sj.w, sp, tref, a0x,
-                                        a0y, a0z, c0);
-              pair_acc<T, TABLE, COUNT>(p1.x - sj.x, p1.y - sj.y, p1.z - sj.z, sj.w, sp, tref, a1x,
-                                        a1y, a1z, c1);
-              if (COUNT) n_in += (v0 ? c0 : 0u) + (v1 ? c1 : 0u);
+              for (int j = kb; j < ke; ++j) {
+                const V4<T> sj = s_src[j];
+                unsigned c0 = 0, c1 = 0;
+                pair_acc<T, TABLE, COUNT>(p0.x - sj.x, p0.y - sj.y, p0.z - sj.z, sj.w, sp, tref, a0x, a0y, a0z,
+                                          c0);
+                pair_acc<T, TABLE, COUNT>(p1.x - sj.x, p1.y - sj.y, p1.z - sj.z, sj.w, sp, tref, a1x, a1y, a1z,
+                                          c1);
+                if (COUNT) n_in += (v0 ? c0 : 0u) + (v1 ? c1 : 0u);
+              }
             }
           }
         }

@@ -62,18 +62,18 @@ static __global__ void k_cell_start(const uint64_t* __restrict__ keys, long long
   cell_start[c] = (int)lo;
 }
 
-// bounding box of every globally aligned tile of kPPTile consecutive (sorted) particles: one warp per
-// tile, 8 coalesced 128-bit loads per lane.  Consumed by the short-range kernel to skip source tiles
+// bounding box of every globally aligned group of kPPSub consecutive (sorted) particles: one warp per
+// group, coalesced 128-bit loads.  Consumed by the short-range kernel to skip source tiles
 // that cannot reach a target group.
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_tile_aabb(const V4<T>* __restrict__ posm, long long n, V4<T>* __restrict__ aabb) {
   const long long tile = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const long long b = tile * kPPTile;
+  const long long b = tile * kPPSub;
   if (b >= n) return;
   T lx = 1e30, ly = 1e30, lz = 1e30, hx = -1e30, hy = -1e30, hz = -1e30;
-  for (int k = lane; k < kPPTile && b + k < n; k += 32) {
+  for (int k = lane; k < kPPSub && b + k < n; k += 32) {
     const V4<T> p = posm[b + k];
     lx = min(lx, p.x), ly = min(ly, p.y), lz = min(lz, p.z);
     hx = max(hx, p.x), hy = max(hy, p.y), hz = max(hz, p.z);
