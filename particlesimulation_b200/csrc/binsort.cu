@@ -34,14 +34,16 @@ int alloc_particles(p3m_ctx* c, long long n) {
   P3M_TRY(dev_alloc(&s.acc_sr, cap));
   P3M_TRY(dev_alloc(&s.id, cap));
   P3M_TRY(dev_alloc(&s.id_alt, cap));
-  P3M_TRY(dev_alloc(&s.keys, cap));
-  P3M_TRY(dev_alloc(&s.keys_alt, cap));
-  P3M_TRY(dev_alloc(&s.slots, cap));
-  P3M_TRY(dev_alloc(&s.slots_alt, cap));
+  // sort scratch: also used for the ghost sort, which can hold up to 2 * cap particles (dist.cu)
+  const long long scap = c->nranks > 1 ? 2 * cap : cap;
+  P3M_TRY(dev_alloc(&s.keys, scap));
+  P3M_TRY(dev_alloc(&s.keys_alt, scap));
+  P3M_TRY(dev_alloc(&s.slots, scap));
+  P3M_TRY(dev_alloc(&s.slots_alt, scap));
   P3M_TRY(dev_alloc(&s.aabb, 2 * (cap / kPPSub + 8)));
   P3M_TRY(dev_alloc(&s.pp_items, 2 * (cap / kPPTargets + ((size_t)1 << (3 * Sel<T>::g(c).mbits)) + 16)));
   size_t tmp = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp, s.keys, s.keys_alt, s.slots, s.slots_alt, (int)cap, 0,
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, s.keys, s.keys_alt, s.slots, s.slots_alt, (int)scap, 0,
                                   64, c->stream);
   if (s.cub_tmp) cudaFree(s.cub_tmp);
   s.cub_tmp = nullptr;

@@ -184,9 +184,17 @@ int dist_migrate(p3m_ctx* c, bool exchange) {
   const int* h = c->dist_counts_host;
   const int* seg = h + kCntSeg;
   long long n_new = h[kCntMine + me];
-  if (exchange)
-    for (int src = 0; src < P; ++src)
-      if (src != me) n_new += h[kCntAll + src * P + me];
+  if (exchange) {
+    // every rank evaluates EVERY rank's capacity from the same all-gathered matrix, so that all of
+    // them fail together instead of one leaving the others waiting in a collective
+    for (int dst = 0; dst < P; ++dst) {
+      long long tot = 0;
+      for (int src = 0; src < P; ++src) tot += h[kCntAll + src * P + dst];
+      if (tot > c->cap)
+        return fail(P3M_ERANGE, "rank %d would hold %lld particles, capacity %lld", dst, tot, c->cap);
+      if (dst == me) n_new = tot;
+    }
+  }
   if (n_new > c->cap)
     return fail(P3M_ERANGE, "rank %d would hold %lld particles, capacity %lld", me, n_new, c->cap);
   if (n > 0) {
@@ -276,14 +284,16 @@ int dist_ghosts(p3m_ctx* c) {
   const int P = c->nranks, me = c->rank;
   ncclComm_t comm = (ncclComm_t)c->nccl_comm;
   const long long ncells = 1LL << (3 * g.mbits);
-  if (s.ghost_cap < c->cap) {
-    P3M_TRY(dev_realloc(&s.gposm, c->cap));
-    P3M_TRY(dev_realloc(&s.gposm_alt, c->cap));
-    P3M_TRY(dev_realloc(&s.gid, c->cap));
-    P3M_TRY(dev_realloc(&s.gid_alt, c->cap));
+  if (s.ghost_cap < 2 * c->cap) {
+    // worst case: one layer holds (almost) every particle of a rank and goes to both neighbours, and
+    // both neighbours' boundary layers arrive here: 2 * cap on each side
+    P3M_TRY(dev_realloc(&s.gposm, 2 * c->cap));
+    P3M_TRY(dev_realloc(&s.gposm_alt, 2 * c->cap));
+    P3M_TRY(dev_realloc(&s.gid, 2 * c->cap));
+    P3M_TRY(dev_realloc(&s.gid_alt, 2 * c->cap));
     P3M_TRY(dev_realloc(&s.gcell_start, ncells + 2));
-    P3M_TRY(dev_realloc(&s.gaabb, 2 * (c->cap / kPPSub + 8)));
-    s.ghost_cap = c->cap;
+    P3M_TRY(dev_realloc(&s.gaabb, 2 * (2 * c->cap / kPPSub + 8)));
+    s.ghost_cap = 2 * c->cap;
   }
   phase_begin(c, PH_COMM);
   const long long n = c->n, half = s.ghost_cap / 2;
@@ -302,8 +312,9 @@ int dist_ghosts(p3m_ctx* c) {
   const long long send_lo = h[2 * me], send_hi = h[2 * me + 1];
   const long long recv_lo = me > 0 ? h[2 * (me - 1) + 1] : 0;      // rank-1's highest layer
   const long long recv_hi = me < P - 1 ? h[2 * (me + 1)] : 0;      // rank+1's lowest layer
-  if (send_lo > half || send_hi > half || recv_lo + recv_hi > s.ghost_cap)
-    return fail(P3M_ERANGE, "ghost layer overflow on rank %d", me);
+  for (int r = 0; r < P; ++r)  // same verdict on every rank (capacities are equal by construction)
+    if (h[2 * r] > half || h[2 * r + 1] > half)
+      return fail(P3M_ERANGE, "ghost layer overflow on rank %d", r);
   P3M_NCCL(ncclGroupStart());
   if (me > 0) {
     if (send_lo > 0) {
