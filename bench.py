@@ -182,6 +182,60 @@ def multi_particles(world, n_per_gpu):
     return np.concatenate(pos), np.concatenate(vel), np.concatenate(mass)
 
 
+def run_mesh_config(args):
+    """Secondary measurement (not the headline line): BASELINE configs[2]-style PM run on ONE GPU --
+    uniform cube, 2^24 particles, 512^3 mesh, TSC, 2-point, discrete-Laplacian Green -- where the mesh
+    kernels (deposit, FFT, gather, sort, integrate) are the whole step.  Prints per-kernel HBM fractions."""
+    from particlesimulation_b200 import capi, ics
+    cu = Cuda(); cu.set_device(0)
+    n = int(os.environ.get("P3M_BENCH_N", 1 << 24))
+    grid = int(os.environ.get("P3M_BENCH_GRID", 512))
+    hbm_peak, peak_src, _ = load_peaks()
+    f32 = np.float32
+    def params(timing):
+        p = capi.default_params()
+        p.nx = p.ny = p.nz = grid
+        p.box[:] = (60.0, 60.0, 60.0)
+        p.H = f32(f32(60.0) / f32(grid // 2))
+        p.DT, p.G = 1.0, 4.5e-3
+        p.assignment, p.fd_scheme, p.greens_function = capi.TSC, capi.TWO_POINT, capi.DISCRETE_LAPLACIAN
+        p.p3m = 0
+        p.timing = int(timing)
+        return p
+    H = float(params(0).H)
+    pos, vel, mass = ics.uniform_cube(n, [2 * H] * 3, [60.0 - 2 * H] * 3, total_mass=1.0, seed=42)
+    out = {}
+    for timing in (0, 1):
+        ctx = capi.Context(params(timing))
+        ctx.set_particles(pos, vel, mass)
+        ctx.green_init(); ctx.force(); ctx.kick(0.5)
+        for _ in range(args.warmup):
+            ctx.step(1)
+        if not timing:
+            a, b = cu.event(), cu.event()
+            cu.record(a, ctx.stream); ctx.step(args.steps); cu.record(b, ctx.stream)
+            out["ms_per_step"] = cu.elapsed_ms(a, b) / args.steps
+        else:
+            ctx.phase_ms(reset=True); ctx.step(args.steps)
+            out["phases"] = {k: v / args.steps for k, v in ctx.phase_ms().items()}
+        ctx.close()
+    M = grid ** 3
+    ph = out["phases"]
+    def hbm(b, ms):
+        g = b / (ms / 1e3) / 1e9 if ms > 0 else 0.0
+        return {"achieved_GBs": round(g, 1), "frac_of_measured_hbm": round(g / hbm_peak, 4), "ms": round(ms, 4), "algorithmic_bytes": b}
+    line = {"metric": "PM particle-steps/s (secondary, mesh-dominated)", "value": n / (out["ms_per_step"] / 1e3),
+            "unit": "particle-steps/s", "n_gpus": 1, "ms_per_step": out["ms_per_step"],
+            "config": {"workload": f"C3-style PM: uniform cube, {n} particles, {grid}^3 mesh, TSC, 2-pt, discrete Laplacian"},
+            "roofline_kernels": {
+                "binSort": hbm(76.0 * n, ph["binSort"]), "spreadMass": hbm(16.0 * n + 8.0 * M, ph["spreadMass"]),
+                "poisson": hbm(18.0 * M, ph["forwardFFT"] + ph["fourierPotential"] + ph["inverseFFT"]),
+                "updateAccelerations": hbm(4.0 * M + 28.0 * n, ph["updateAccelerations"]),
+                "integrate": hbm(96.0 * n, ph["integrate"])},
+            "hbm_peak": hbm_peak, "hbm_peak_source": peak_src}
+    print(json.dumps(line))
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -492,11 +546,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c2", choices=["c2", "mesh"],
+                    help="c2 = the headline workload; mesh = secondary mesh-dominated PM run (1 GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         if int(os.environ.get("RANK", 0)) != 0:
             return
         run_reference(args)
+        return
+    if args.config == "mesh":
+        run_mesh_config(args)
         return
     run_ours(args)
 
