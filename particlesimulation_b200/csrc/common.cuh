@@ -187,9 +187,8 @@ constexpr int kTileMinCount = 24;    // segments shorter than this take the dire
 constexpr int kMaxTileBytes = 12288; // per-warp deposit tile budget
 constexpr int kSRTable = 500;        // tabulatedValuesCnt (source/p3mMethod.cpp:42)
 constexpr int kDenseCell = 64;       // chaining cells with >= this many particles use the tiled PP kernel
-constexpr int kPPTargets = 256;      // targets per tiled-PP work item (2 per thread, 128 threads)
-constexpr int kPPTile = 256;         // particles per staged source tile (globally aligned)
-constexpr int kPPSub = 64;           // particles per bounding box (4 boxes per tile): culling granularity
+constexpr int kPPTargets = 64;       // targets per dense-cell work item (one warp, 2 per lane)
+constexpr int kPPSub = 64;           // particles per bounding box / staged source group (globally aligned)
 constexpr int kSubBits = 3;          // 8^3 sub-cells per chaining cell in the sort key
 
 }  // namespace p3m

@@ -13,13 +13,14 @@
 // acceleration mj * f(r) * r_ij is accumulated directly (the reference's  mi*mj*f / mi).
 //
 //   dense cells (>= kDenseCell particles; the Plummer core puts ~half of all particles in 8 cells):
-//     work item = (cell, 256 consecutive targets), 128 threads x 2 targets in registers.  Particles are
-//     sorted by (cell, 8^3 sub-cell, id), so 256 consecutive particles are spatially compact; every
-//     globally aligned 256-particle tile carries a bounding box (k_tile_aabb) and a source tile whose
-//     box is farther than the cutoff from the target group's box is skipped WHOLE (this is exact: it
-//     only drops pairs with r >= re).  Surviving tiles are staged in shared memory and read back with
-//     broadcast LDS.128.  Items are generated on the device, sorted by cost (heaviest first) and
-//     pulled from an atomic queue by a persistent grid.
+//     work item = (cell, 64 consecutive targets) handled by ONE WARP, 2 targets per lane in registers.
+//     Particles are sorted by (cell, 8^3 sub-cell, id), so 64 consecutive particles are spatially
+//     compact; every globally aligned 64-particle group carries a bounding box (k_tile_aabb) and a
+//     source group whose box is farther than the cutoff from the box of the warp's targets is skipped
+//     WHOLE (exact: it only drops pairs with r >= re).  Surviving groups are staged in the warp's
+//     private shared-memory slice (next one prefetched in registers) and read back with broadcast
+//     LDS.128; there is no block-wide barrier in the loop.  Items are generated on the device, sorted
+//     by cost (heaviest first) and pulled from an atomic queue by a persistent grid.
 //   sparse cells: one thread per target walks its 27 cells straight from L1/L2.
 //
 // Force law (code units, G = 1/(4 pi)): table mode reproduces shortRangeForceFromTable
@@ -151,43 +152,45 @@ __global__ void k_pp_items(const int* __restrict__ cell_start, Geom<T> g, int* _
   }
 }
 
+// Dense cells.  Every WARP is autonomous: it pulls (cell, 64 targets) items from the atomic queue, holds
+// 2 targets per lane in registers, tests 32 source boxes (64 particles each) per ballot against the box
+// of its own targets, stages each surviving box in its private shared-memory slice (next box prefetched
+// into registers meanwhile) and runs the 64-source inner loop with broadcast LDS.128.  No block-wide
+// barrier in the loop: the 4 warps of a CTA only share the force table.
 template <typename T, bool TABLE, bool COUNT>
-__global__ void __launch_bounds__(128, 8)
+__global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 8)
 k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
            const V4<T>* __restrict__ aabb, const V4<T>* __restrict__ gposm,
            const int* __restrict__ gcell_start, const V4<T>* __restrict__ gaabb,
-           const int* __restrict__ items,
-           const unsigned* __restrict__ order, int* __restrict__ counters, Geom<T> g, SRParams<T> sp,
-           const T* __restrict__ g_tab, V4<T>* __restrict__ acc, V4<T>* __restrict__ acc_sr,
+           const int* __restrict__ items, const unsigned* __restrict__ order,
+           int* __restrict__ counters, Geom<T> g, SRParams<T> sp, const T* __restrict__ g_tab,
+           V4<T>* __restrict__ acc, V4<T>* __restrict__ acc_sr,
            unsigned long long* __restrict__ pair_counts) {
   __shared__ V2<T> s_tab[kSRTable];
-  __shared__ V4<T> s_src[kPPTile];
-  __shared__ T s_box[4][6];
-  __shared__ int s_item;
+  __shared__ V4<T> s_src_all[4][kPPSub];
   __shared__ unsigned s_tb;
   load_table(g_tab, s_tab);
   TableRef<T> tref(s_tab, &s_tb);
   __syncthreads();
   tref.finish(&s_tb);
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  V4<T>* s_src = s_src_all[wid];
   const int nitems = counters[0];
   const T cut2 = sp.re2 * (T(1) + T(1e-5));
   unsigned long long checked = 0, inrange = 0;
   for (;;) {
-    __syncthreads();
-    if (tid == 0) s_item = atomicAdd(&counters[1], 1);
-    __syncthreads();
-    const int it = s_item;
+    int it = 0;
+    if (lane == 0) it = atomicAdd(&counters[1], 1);
+    it = __shfl_sync(0xffffffffu, it, 0);
     if (it >= nitems) break;
     const int item = (int)order[it];
     const uint32_t q = (uint32_t)items[2 * item];
     const int t0 = items[2 * item + 1];
     const int tend = min(cell_start[q + 1], t0 + kPPTargets);
-    // warp w owns targets [t0 + 64 w, t0 + 64 w + 64): lane l holds 64 w + l and 64 w + 32 + l
-    const int i0 = t0 + 64 * wid + lane, i1 = i0 + 32;
+    const int i0 = t0 + lane, i1 = i0 + 32;
     const bool v0 = i0 < tend, v1 = i1 < tend;
     const V4<T> p0 = posm[v0 ? i0 : t0], p1 = posm[v1 ? i1 : t0];
-    // bounding boxes (code units): of this warp's 64 targets (registers) and of the whole group (smem)
+    // bounding box of this warp's targets (code units)
     T wlo[3], whi[3];
     {
       T lx = min(p0.x, p1.x), ly = min(p0.y, p1.y), lz = min(p0.z, p1.z);
@@ -198,17 +201,6 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
         hy = max(hy, __shfl_xor_sync(0xffffffffu, hy, o)), hz = max(hz, __shfl_xor_sync(0xffffffffu, hz, o));
       }
       wlo[0] = lx, wlo[1] = ly, wlo[2] = lz, whi[0] = hx, whi[1] = hy, whi[2] = hz;
-      if (lane == 0) {
-        s_box[wid][0] = lx, s_box[wid][1] = ly, s_box[wid][2] = lz;
-        s_box[wid][3] = hx, s_box[wid][4] = hy, s_box[wid][5] = hz;
-      }
-    }
-    __syncthreads();
-    T tlo[3], thi[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      tlo[d] = min(min(s_box[0][d], s_box[1][d]), min(s_box[2][d], s_box[3][d]));
-      thi[d] = max(max(s_box[0][d + 3], s_box[1][d + 3]), max(s_box[2][d + 3], s_box[3][d + 3]));
     }
     T a0x = 0, a0y = 0, a0z = 0, a1x = 0, a1y = 0, a1z = 0;
     unsigned n_in = 0;
@@ -226,39 +218,45 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
           const V4<T>* __restrict__ sbb = own ? aabb : gaabb;
           const int s = scs[qn], e = scs[qn + 1];
           if (s >= e) continue;
-          for (int tile = s / kPPTile; tile <= (e - 1) / kPPTile; ++tile) {
-            // exact culling on the 4 bounding boxes (64 particles each) of this tile: lanes 0..3 test one
-            // box each against the group's box (all warps agree -> CTA-uniform skip of the staging) and
-            // against this warp's own box (warp-uniform skip of the 64-source inner loop)
-            T dg = T(1e30), dw = T(1e30);
-            const int sub = tile * (kPPTile / kPPSub) + lane;
-            if (lane < kPPTile / kPPSub && sub * kPPSub < e && (sub + 1) * kPPSub > s) {
-              const V4<T> blo = sbb[2 * sub], bhi = sbb[2 * sub + 1];
-              T gx = max(T(0), max(blo.x - thi[0], tlo[0] - bhi.x));
-              T gy = max(T(0), max(blo.y - thi[1], tlo[1] - bhi.y));
-              T gz = max(T(0), max(blo.z - thi[2], tlo[2] - bhi.z));
-              dg = gx * gx + gy * gy + gz * gz;
-              gx = max(T(0), max(blo.x - whi[0], wlo[0] - bhi.x));
-              gy = max(T(0), max(blo.y - whi[1], wlo[1] - bhi.y));
-              gz = max(T(0), max(blo.z - whi[2], wlo[2] - bhi.z));
-              dw = gx * gx + gy * gy + gz * gz;
+          const int box_first = s / kPPSub, box_last = (e - 1) / kPPSub;
+          for (int b0 = box_first; b0 <= box_last; b0 += 32) {
+            // exact culling, 32 boxes per ballot: a box farther than the cutoff from the targets' box
+            // holds no partner of any of them
+            const int mybox = b0 + lane;
+            bool near_ = false;
+            if (mybox <= box_last) {
+              const V4<T> blo = sbb[2 * mybox], bhi = sbb[2 * mybox + 1];
+              const T gx = max(T(0), max(blo.x - whi[0], wlo[0] - bhi.x));
+              const T gy = max(T(0), max(blo.y - whi[1], wlo[1] - bhi.y));
+              const T gz = max(T(0), max(blo.z - whi[2], wlo[2] - bhi.z));
+              near_ = gx * gx + gy * gy + gz * gz <= cut2;
             }
-            if (__ballot_sync(0xffffffffu, dg <= cut2) == 0u) continue;  // CTA-uniform
-            const unsigned near = __ballot_sync(0xffffffffu, dw <= cut2);
-            const int jb = max(s, tile * kPPTile), je = min(e, (tile + 1) * kPPTile);
-            __syncthreads();
-            const int j0 = jb + tid, j1 = jb + 128 + tid;
-            if (j0 < je) s_src[tid] = spos[j0];
-            if (j1 < je) s_src[tid + 128] = spos[j1];
-            __syncthreads();
-#pragma unroll 1
-            for (int k = 0; k < kPPTile / kPPSub; ++k) {
-              if (!((near >> k) & 1u)) continue;  // warp-uniform
-              const int kb = max(jb, (tile * (kPPTile / kPPSub) + k) * kPPSub) - jb;
-              const int ke = min(je, (tile * (kPPTile / kPPSub) + k + 1) * kPPSub) - jb;
-              if (COUNT) checked += (unsigned long long)max(ke - kb, 0) * ((v0 ? 1 : 0) + (v1 ? 1 : 0));
-#pragma unroll 4
-              for (int j = kb; j < ke; ++j) {
+            unsigned todo = __ballot_sync(0xffffffffu, near_);
+            if (todo == 0u) continue;
+            // software pipeline over the surviving boxes: registers hold the NEXT box while the
+            // current one is consumed from shared memory
+            int k = __ffs(todo) - 1;
+            todo &= todo - 1;
+            int jb = max(s, (b0 + k) * kPPSub), je = min(e, (b0 + k + 1) * kPPSub);
+            V4<T> n0 = (jb + lane < je) ? spos[jb + lane] : V4<T>{0, 0, 0, 0};
+            V4<T> n1 = (jb + 32 + lane < je) ? spos[jb + 32 + lane] : V4<T>{0, 0, 0, 0};
+            for (;;) {
+              const int cnt = je - jb;
+              __syncwarp();
+              s_src[lane] = n0;
+              s_src[lane + 32] = n1;
+              __syncwarp();
+              const bool more = todo != 0u;
+              if (more) {
+                k = __ffs(todo) - 1;
+                todo &= todo - 1;
+                jb = max(s, (b0 + k) * kPPSub), je = min(e, (b0 + k + 1) * kPPSub);
+                n0 = (jb + lane < je) ? spos[jb + lane] : V4<T>{0, 0, 0, 0};
+                n1 = (jb + 32 + lane < je) ? spos[jb + 32 + lane] : V4<T>{0, 0, 0, 0};
+              }
+              if (COUNT) checked += (unsigned long long)cnt * ((v0 ? 1 : 0) + (v1 ? 1 : 0));
+#pragma unroll 8
+              for (int j = 0; j < cnt; ++j) {
                 const V4<T> sj = s_src[j];
                 unsigned c0 = 0, c1 = 0;
                 pair_acc<T, TABLE, COUNT>(p0.x - sj.x, p0.y - sj.y, p0.z - sj.z, sj.w, sp, tref, a0x, a0y, a0z,
@@ -267,6 +265,7 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
                                           c1);
                 if (COUNT) n_in += (v0 ? c0 : 0u) + (v1 ? c1 : 0u);
               }
+              if (!more) break;
             }
           }
         }
