@@ -260,6 +260,8 @@ int bin_sort(p3m_ctx* c) {
   if (g.p3m) {
     g.sbits = kSubBits;
     while (g.sbits > 0 && 3 * g.mbits + 3 * g.sbits + idbits > 62) --g.sbits;
+  } else if (3 * g.mbits + 3 * g.tile_shift + idbits <= 62) {
+    g.sbits = g.tile_shift;  // PM: sub key = mesh cell inside the tile (sort_kernels.cuh)
   }
   const int keybits = idbits + 3 * g.sbits + 3 * g.mbits;
   const long long ncells = 1LL << (3 * g.mbits);

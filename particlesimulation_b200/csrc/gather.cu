@@ -77,17 +77,15 @@ __device__ __forceinline__ void add_external(const Geom<T>& g, T x, T y, T z, T&
 }
 
 template <typename T, int K, int FD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_gather(const V4<T>* __restrict__ posm, long long n, int chunk, const int* __restrict__ cell_start,
          Geom<T> g, const T* __restrict__ phi, V4<T>* __restrict__ acc) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(32) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int tile_cap = g.tex * g.tey * g.tez;
-  const int pcap = (g.tex + 2 * FD) * (g.tey + 2 * FD) * (g.tez + 2 * FD);
-  T* sphi = reinterpret_cast<T*>(smem_raw);
-  T* sEx = sphi + pcap;
-  T* sEy = sEx + tile_cap;
-  T* sEz = sEy + tile_cap;
+  // E tile as (Ex, Ey, Ez, -) records: one vector LDS per stencil point; potential tile behind it
+  V4<T>* sE = reinterpret_cast<V4<T>*>(smem_raw);
+  T* sphi = reinterpret_cast<T*>(sE + tile_cap);
   long long cur = (long long)blockIdx.x * chunk;
   const long long chunk_end = min(n, cur + (long long)chunk);
   const long long ncells = 1LL << (3 * g.mbits);
@@ -156,7 +154,7 @@ k_gather(const V4<T>* __restrict__ posm, long long n, int chunk, const int* __re
           fy = k * (-c0[2 * sy] + 8 * c0[sy] - 8 * c0[-sy] + c0[-2 * sy]);
           fz = k * (-c0[2 * sz] + 8 * c0[sz] - 8 * c0[-sz] + c0[-2 * sz]);
         }
-        sEx[e] = fx, sEy[e] = fy, sEz[e] = fz;
+        sE[e] = V4<T>{fx, fy, fz, 0};
       }
     }
     __syncthreads();
@@ -178,8 +176,8 @@ k_gather(const V4<T>* __restrict__ posm, long long n, int chunk, const int* __re
 #pragma unroll
             for (int cc = 0; cc < K; ++cc) {
               const T w = scale * ((s.wx[a] * s.wy[b]) * s.wz[cc]);
-              const int e = base + (cc * ext[1] + b) * ext[0] + a;
-              ax += w * sEx[e], ay += w * sEy[e], az += w * sEz[e];
+              const V4<T> ev = sE[base + (cc * ext[1] + b) * ext[0] + a];
+              ax += w * ev.x, ay += w * ev.y, az += w * ev.z;
             }
       } else {
         gather_direct<T, K, FD>(s, g, phi, ax, ay, az);
@@ -203,7 +201,7 @@ static int launch_gather(p3m_ctx* c) {
   if (chunk > kGatherChunk) chunk = kGatherChunk;
   const long long blocks = (n + chunk - 1) / chunk;
   const size_t smem = sizeof(T) * ((size_t)(g.tex + 2 * FD) * (g.tey + 2 * FD) * (g.tez + 2 * FD) +
-                                   3 * (size_t)g.tex * g.tey * g.tez);
+                                   4 * (size_t)g.tex * g.tey * g.tez);
   auto kern = k_gather<T, K, FD>;
   P3M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)blocks, 256, smem, c->stream>>>(s.posm, n, chunk, s.cell_start, g, s.potential,

@@ -19,7 +19,13 @@ __global__ void k_keys(const V4<T>* __restrict__ posm, const int* __restrict__ i
   bin_cell(g, p.x, p.y, p.z, cx, cy, cz, inside);
   if (!inside) flags[1] = 1;
   uint64_t m = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
-  if (g.sbits) {
+  if (g.sbits && !g.p3m) {
+    // PM only: the mesh cell inside the 8^3 tile, x fastest -- neighbouring lanes then touch
+    // neighbouring shared-memory words in the deposit / gather tiles
+    const int mask = (1 << g.tile_shift) - 1;
+    const int lx = ((int)p.x) & mask, ly = ((int)p.y) & mask, lz = ((int)p.z) & mask;
+    m = (m << (3 * g.sbits)) | (uint64_t)((lz << (2 * g.tile_shift)) | (ly << g.tile_shift) | lx);
+  } else if (g.sbits) {
     // position inside the chaining cell in units of 1/2^sbits of the cell: x/HC - cx is exact in
     // floating point (cx is the truncation of the same quotient), so the sub-cell is reproducible
     const int S = 1 << g.sbits;
