@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libp3m_b200.so")
+# P3M_B200_LIB: A/B-testing hook for an alternatively tuned build of the same library
+LIB_PATH = os.environ.get("P3M_B200_LIB") or os.path.join(_HERE, "libp3m_b200.so")
 
 NGP, CIC, TSC = 0, 1, 2
 TWO_POINT, FOUR_POINT = 0, 1

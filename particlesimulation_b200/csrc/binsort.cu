@@ -8,6 +8,9 @@
 // records, so every cell is a contiguous, id-ordered slice of the particle arrays.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "ctx.cuh"
 #include "sort_kernels.cuh"
 
@@ -106,6 +109,16 @@ int upload_particles(p3m_ctx* c, const float* pos, const float* vel, const float
   c->n_global = n;
   c->have_particles = true;
   c->sorted = false;
+  {
+    // equal masses?  (positive floats order like their bit patterns)
+    float lo = n > 0 ? mass[0] : 0.f, hi = lo;
+    for (long long i = 1; i < n; ++i) lo = mass[i] < lo ? mass[i] : lo, hi = mass[i] > hi ? mass[i] : hi;
+    c->mass_lo = lo, c->mass_hi = hi;
+    c->uniform_mass = n > 0 && lo == hi && lo > 0.f;
+    T m = (T)lo;
+    if (units == P3M_UNITS_ORIGINAL) m = mf * m;
+    c->uniform_mass_code = (double)m;
+  }
   // multi-GPU: every rank was handed the whole set; keep the particles of this rank's z-slab
   if (c->nranks > 1) P3M_TRY(dist_migrate<T>(c, false));
   return 0;
@@ -131,6 +144,27 @@ int upload_particles_ids(p3m_ctx* c, const float* pos, const float* vel, const f
   c->nranks = nr;
   if (r != 0) return r;
   c->n_global = ng;
+  if (nr > 1) {
+    // the subset may be uniform while the global set is not: agree on min / max over all ranks
+    int v[2] = {-0x7fffffff, -0x7fffffff};
+    if (n > 0 && c->mass_lo > 0.f) {
+      memcpy(&v[0], &c->mass_hi, 4);
+      int lo_bits;
+      memcpy(&lo_bits, &c->mass_lo, 4);
+      v[1] = -lo_bits;
+    } else if (n > 0) {
+      v[0] = 0x7fffffff, v[1] = 0;  // non-positive mass somewhere: never uniform
+    }
+    P3M_TRY(dist_allreduce_host_imax(c, v, 2));
+    c->uniform_mass = v[0] == -v[1] && v[0] > 0;
+    if (c->uniform_mass) {
+      float mg;
+      memcpy(&mg, &v[0], 4);
+      T m = (T)mg;
+      if (units == P3M_UNITS_ORIGINAL) m = (c->f64 ? (T)c->mass_factor64 : (T)c->mass_factor32) * m;
+      c->uniform_mass_code = (double)m;
+    }
+  }
   State<T>& s = Sel<T>::st(c);
   if (n > 0) {
     int32_t* stage = nullptr;
@@ -259,6 +293,7 @@ int bin_sort(p3m_ctx* c) {
   g.sbits = 0;
   if (g.p3m) {
     g.sbits = kSubBits;
+    if (const char* e = getenv("P3M_TUNE_SUBBITS")) g.sbits = atoi(e);  // tuning hook (measurements only)
     while (g.sbits > 0 && 3 * g.mbits + 3 * g.sbits + idbits > 62) --g.sbits;
   } else if (3 * g.mbits + 3 * g.tile_shift + idbits <= 62) {
     g.sbits = g.tile_shift;  // PM: sub key = mesh cell inside the tile (sort_kernels.cuh)

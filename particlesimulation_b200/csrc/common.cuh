@@ -188,7 +188,10 @@ constexpr int kMaxTileBytes = 12288; // per-warp deposit tile budget
 constexpr int kSRTable = 500;        // tabulatedValuesCnt (source/p3mMethod.cpp:42)
 constexpr int kDenseCell = 64;       // chaining cells with >= this many particles use the tiled PP kernel
 constexpr int kPPTargets = 64;       // targets per dense-cell work item (one warp, 2 per lane)
-constexpr int kPPSub = 64;           // particles per bounding box / staged source group (globally aligned)
-constexpr int kSubBits = 3;          // 8^3 sub-cells per chaining cell in the sort key
+#ifndef P3M_PP_SUB
+#define P3M_PP_SUB 32
+#endif
+constexpr int kPPSub = P3M_PP_SUB;           // particles per bounding box / staged source group (globally aligned)
+constexpr int kSubBits = 4;          // 16^3 sub-cells per chaining cell in the sort key
 
 }  // namespace p3m

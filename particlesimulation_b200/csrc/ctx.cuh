@@ -78,6 +78,12 @@ struct p3m_ctx {
   p3m::PhaseTimer timer;
   bool timing = false;
   int count_pairs = 0;
+  // all particle masses equal (true for every sampler of the reference: masses = M / n); lets the
+  // short-range kernel fold the mass into its force table.  Decided on the host at upload time over the
+  // GLOBAL particle set (multi-GPU: all-reduced), value in code units.
+  bool uniform_mass = false;
+  double uniform_mass_code = 0;
+  float mass_lo = 0, mass_hi = 0;
   // multi-GPU (z-slabs of particles, NCCL): dist.cu
   void* nccl_comm = nullptr;  // ncclComm_t
   int rank = 0, nranks = 1;
@@ -153,6 +159,7 @@ template <typename T> int dist_migrate(p3m_ctx* c, bool exchange);
 template <typename T> int dist_ghosts(p3m_ctx* c);
 template <typename T> int dist_allreduce_density(p3m_ctx* c);
 int dist_allreduce(p3m_ctx* c, void* buf, size_t count, int kind /*0 int max, 1 double sum*/);
+int dist_allreduce_host_imax(p3m_ctx* c, int* v, int count /* <= 8 */);
 template <typename T> int upload_particles_ids(p3m_ctx* c, const float* pos, const float* vel, const float* mass, const int32_t* ids, long long n, int units);
 template <typename T> int download_local(p3m_ctx* c, int32_t* ids, float* pos, float* vel, float* acc, int units);
 template <typename T, typename O> int get_mesh(p3m_ctx* c, const T* dev, O* out, long long count);

@@ -112,6 +112,17 @@ int dist_allreduce(p3m_ctx* c, void* buf, size_t count, int kind) {
   return 0;
 }
 
+// small host-side integer max over the ranks (blocking)
+int dist_allreduce_host_imax(p3m_ctx* c, int* v, int count) {
+  if (c->nranks <= 1) return 0;
+  int* d = c->dist_counts + 120;
+  P3M_CUDA(cudaMemcpyAsync(d, v, sizeof(int) * count, cudaMemcpyHostToDevice, c->stream));
+  P3M_TRY(dist_allreduce(c, d, (size_t)count, 0));
+  P3M_CUDA(cudaMemcpyAsync(v, d, sizeof(int) * count, cudaMemcpyDeviceToHost, c->stream));
+  P3M_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 template <typename T>
 int dist_allreduce_density(p3m_ctx* c) {
   if (c->nranks <= 1) return 0;

@@ -63,51 +63,84 @@ __device__ __forceinline__ T ref_force_dev(const SRParams<T>& sp, T r) {
   return G / (r * r);
 }
 
-// Handle of the shared-memory table of (A_t, B_t) pairs.
-// fp32: a round-toward-zero add of 2^23 leaves floor(xi) in the low mantissa bits; the exponent bits
-// (0x4B000000) are folded into an opaque pre-biased base, so the lookup is FADD.RZ + LEA + LDS.64.
-template <typename T>
+// Handle of the shared-memory table of (A_t, B_t) pairs, replicated COPIES times so that the lanes of a
+// warp read disjoint banks: entry t of copy c sits at element t * COPIES + c and lane l uses copy
+// l % COPIES.  A 64-bit (fp32 pair) load is served one half warp at a time, a 128-bit (fp64 pair) load
+// one quarter warp at a time, so 128 / sizeof(pair) copies make EVERY lookup conflict-free (ncu on the
+// single-copy table: 41 % of all shared-memory wavefronts were bank conflicts of this lookup and the
+// kernel sat at 0.86 wavefronts/clk/SM, i.e. it was shared-memory bound).
+// The argument is u = r^2 / re^2 saturated to [0, 1]:  index = floor(499 u), value = A + B u.
+// fp32: fma.rz(u, 499, 2^23) leaves the index in the low mantissa bits; the exponent bits (0x4B000000)
+// are folded into an opaque pre-biased per-lane base, so the lookup is FFMA.RZ + LEA + LDS.64.
+template <typename T, int COPIES>
 struct TableRef;
-template <>
-struct TableRef<float> {
+template <int COPIES>
+struct TableRef<float, COPIES> {
+  static constexpr int kShift = 3 + (COPIES == 1 ? 0 : COPIES == 8 ? 3 : 4);
+  static_assert(COPIES == 1 || COPIES == 8 || COPIES == 16, "copies");
   unsigned base;
-  // `slot` is a shared-memory word: the biased base makes a round trip through it so that ptxas cannot
-  // re-associate the bias back out of the address arithmetic (it would cost an IADD3 per pair).
+  // `slots` are 32 shared-memory words: the biased base makes a round trip through them so that ptxas
+  // cannot re-associate the bias back out of the address arithmetic (it would cost an IADD3 per pair).
   // Must be called by all threads of the block, before a __syncthreads().
-  __device__ __forceinline__ TableRef(const V2<float>* tab, volatile unsigned* slot) {
-    if (threadIdx.x == 0) *slot = (unsigned)__cvta_generic_to_shared(tab) - (0x4B000000u << 3);
+  __device__ __forceinline__ TableRef(const V2<float>* tab, volatile unsigned* slots) {
+    if (threadIdx.x < 32)
+      slots[threadIdx.x] = (unsigned)__cvta_generic_to_shared(tab) + (threadIdx.x & (COPIES - 1)) * 8u -
+                           (0x4B000000u << kShift);
     base = 0;
   }
-  __device__ __forceinline__ void finish(volatile unsigned* slot) { base = *slot; }
-  __device__ __forceinline__ V2<float> get(float xi) const {  // 0 <= xi <= 499
-    const unsigned addr = base + ((unsigned)__float_as_int(__fadd_rz(xi, 8388608.0f)) << 3);
+  __device__ __forceinline__ void finish(volatile unsigned* slots) { base = slots[threadIdx.x & 31]; }
+  __device__ __forceinline__ V2<float> get(float u) const {  // 0 <= u <= 1
+    const unsigned addr =
+        base + ((unsigned)__float_as_int(__fmaf_rz(u, float(kSRTable - 1), 8388608.0f)) << kShift);
     V2<float> e;
     asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(e.x), "=f"(e.y) : "r"(addr));
     return e;
   }
 };
-template <>
-struct TableRef<double> {
+template <int COPIES>
+struct TableRef<double, COPIES> {
   const V2<double>* tab;
-  __device__ __forceinline__ TableRef(const V2<double>* t, volatile unsigned*) : tab(t) {}
+  __device__ __forceinline__ TableRef(const V2<double>* t, volatile unsigned*)
+      : tab(t + (threadIdx.x & (COPIES - 1))) {}
   __device__ __forceinline__ void finish(volatile unsigned*) {}
-  __device__ __forceinline__ V2<double> get(double xi) const { return tab[(int)xi]; }
+  __device__ __forceinline__ V2<double> get(double u) const {
+    return tab[(int)(u * double(kSRTable - 1)) * COPIES];
+  }
 };
 
-// One target-source pair, d = target - source in code units.
-template <typename T, bool TABLE, bool COUNT>
+template <typename T>
+__device__ __forceinline__ T fma_sat(T a, T b, T c) {
+  return fmin(fma(a, b, c), T(1));
+}
+template <>
+__device__ __forceinline__ float fma_sat<float>(float a, float b, float c) {
+  float r;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// One target-source pair.
+//  TABLE: d = (target - source) / re, so u = |d|^2 = r^2 / re^2 saturates to 1 exactly at the cutoff,
+//         where the last table entry is (0, 0): that folds the test r^2 < re^2 of
+//         source/p3mMethod.cpp:258 into the lookup.  The table holds re * (A_t, 499 B_t) [* m when all
+//         masses are equal], so  acc += f * d  needs no rescaling.  Per pair: 3 FADD, FMUL, FFMA,
+//         FFMA.SAT, FFMA.RZ, LEA, LDS.64, FFMA, (FMUL mj), 3 FFMA = 13 (14) issue slots.
+//  analytic: d in code units (shortRangeForce :220-238, divided by mi).
+template <typename T, bool TABLE, bool COUNT, bool UNIMASS, int COPIES>
 __device__ __forceinline__ void pair_acc(T dx, T dy, T dz, T mj, const SRParams<T>& sp,
-                                         const TableRef<T>& tab, T& ax, T& ay, T& az,
+                                         const TableRef<T, COPIES>& tab, T& ax, T& ay, T& az,
                                          unsigned& n_in) {
-  const T r2 = dx * dx + dy * dy + dz * dz;
-  if (COUNT) n_in += (r2 < sp.re2 && r2 > T(0)) ? 1u : 0u;
   if (TABLE) {
-    const T xi = fmin(r2 * sp.inv_delta2, T(kSRTable - 1));
-    const V2<T> e = tab.get(xi);
-    const T f = mj * (e.x + e.y * xi);
-    ax += f * dx, ay += f * dy, az += f * dz;
+    const T u = fma_sat<T>(dz, dz, fma(dy, dy, dx * dx));
+    if (COUNT) n_in += (u < T(1) && u > T(0)) ? 1u : 0u;
+    const V2<T> e = tab.get(u);
+    T f = fma(e.y, u, e.x);
+    if (!UNIMASS) f *= mj;
+    ax = fma(f, dx, ax), ay = fma(f, dy, ay), az = fma(f, dz, az);
   } else {
-    if (r2 < sp.re2 && r2 > T(0)) {  // shortRangeForce :220-238, divided by mi
+    const T r2 = dx * dx + dy * dy + dz * dz;
+    if (COUNT) n_in += (r2 < sp.re2 && r2 > T(0)) ? 1u : 0u;
+    if (r2 < sp.re2 && r2 > T(0)) {
       const T r = sqrt(r2);
       const T G = T(0.07957747154594767);
       const T f = mj * (ref_force_dev(sp, r) - G / (r2 + sp.eps2)) / r;
@@ -116,9 +149,14 @@ __device__ __forceinline__ void pair_acc(T dx, T dy, T dz, T mj, const SRParams<
   }
 }
 
-template <typename T>
-__device__ __forceinline__ void load_table(const T* __restrict__ g_tab, V2<T>* s_tab) {
-  for (int t = threadIdx.x; t < kSRTable; t += blockDim.x) s_tab[t] = V2<T>{g_tab[2 * t], g_tab[2 * t + 1]};
+// g_tab holds the reference's interpolation in slope-intercept form (A_t, B_t) over xi = r^2/delta^2;
+// shared memory gets it over u = xi / 499 with the output scale folded in.
+template <typename T, int COPIES>
+__device__ __forceinline__ void load_table(const T* __restrict__ g_tab, V2<T>* s_tab, T scale) {
+  for (int k = threadIdx.x; k < kSRTable * COPIES; k += blockDim.x) {
+    const int t = k / COPIES;
+    s_tab[k] = V2<T>{g_tab[2 * t] * scale, g_tab[2 * t + 1] * (scale * T(kSRTable - 1))};
+  }
 }
 
 // ---- work items for the dense cells ------------------------------------------------------------------
@@ -152,29 +190,49 @@ __global__ void k_pp_items(const int* __restrict__ cell_start, Geom<T> g, int* _
   }
 }
 
+template <typename T>
+struct PPCfg {
+  static constexpr int kCopies = 128 / (2 * (int)sizeof(T));  // conflict-free table replication
+  static constexpr int kWarps = 16;                            // warps per CTA
+  static constexpr int kCtasPerSm = sizeof(T) == 8 ? 1 : 2;
+  static constexpr size_t smem(int sub) {
+    return sizeof(T) * 2 * kSRTable * kCopies + sizeof(T) * 4 * (size_t)sub * kWarps + 128;
+  }
+};
+
 // Dense cells.  Every WARP is autonomous: it pulls (cell, 64 targets) items from the atomic queue, holds
-// 2 targets per lane in registers, tests 32 source boxes (64 particles each) per ballot against the box
+// 2 targets per lane in registers, tests 32 source boxes (SUB particles each) per ballot against the box
 // of its own targets, stages each surviving box in its private shared-memory slice (next box prefetched
-// into registers meanwhile) and runs the 64-source inner loop with broadcast LDS.128.  No block-wide
-// barrier in the loop: the 4 warps of a CTA only share the force table.
-template <typename T, bool TABLE, bool COUNT>
-__global__ void __launch_bounds__(128, sizeof(T) == 8 ? 4 : 8)
+// into registers meanwhile) and runs the inner loop with broadcast LDS.128.  No block-wide barrier in
+// the loop: the warps of a CTA only share the replicated force table.
+// Staged coordinates are (p - origin) / re with origin = a multiple of 4 below the 27-cell neighbourhood:
+// the subtraction is exact in fp32 (same binade grid, result < 16), the one rounding of the scaling is
+// 2^-24 relative to a number <= 11 / re.
+template <typename T, bool TABLE, bool COUNT, bool UNIMASS, int SUB>
+__global__ void __launch_bounds__(PPCfg<T>::kWarps * 32, PPCfg<T>::kCtasPerSm)
 k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
            const V4<T>* __restrict__ aabb, const V4<T>* __restrict__ gposm,
            const int* __restrict__ gcell_start, const V4<T>* __restrict__ gaabb,
            const int* __restrict__ items, const unsigned* __restrict__ order,
            int* __restrict__ counters, Geom<T> g, SRParams<T> sp, const T* __restrict__ g_tab,
-           V4<T>* __restrict__ acc, V4<T>* __restrict__ acc_sr,
+           T uni_mass, V4<T>* __restrict__ acc, V4<T>* __restrict__ acc_sr,
            unsigned long long* __restrict__ pair_counts) {
-  __shared__ V2<T> s_tab[kSRTable];
-  __shared__ V4<T> s_src_all[4][kPPSub];
-  __shared__ unsigned s_tb;
-  load_table(g_tab, s_tab);
-  TableRef<T> tref(s_tab, &s_tb);
+  constexpr int COPIES = PPCfg<T>::kCopies;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  V2<T>* s_tab = reinterpret_cast<V2<T>*>(smem_raw);
+  V4<T>* s_src_all = reinterpret_cast<V4<T>*>(smem_raw + sizeof(V2<T>) * kSRTable * COPIES);
+  volatile unsigned* s_tb =
+      reinterpret_cast<volatile unsigned*>(smem_raw + sizeof(V2<T>) * kSRTable * COPIES +
+                                           sizeof(V4<T>) * SUB * PPCfg<T>::kWarps);
+  // acc = sum F(u) * (pi - pj) = re * sum F(u) * d
+  const T re = sqrt(sp.re2);
+  const T scl = TABLE ? T(1) / re : T(1);
+  load_table<T, COPIES>(g_tab, s_tab, (TABLE ? re : T(1)) * (UNIMASS ? uni_mass : T(1)));
+  TableRef<T, COPIES> tref(s_tab, s_tb);
   __syncthreads();
-  tref.finish(&s_tb);
+  tref.finish(s_tb);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  V4<T>* s_src = s_src_all[wid];
+  V4<T>* s_src = s_src_all + wid * SUB;
   const int nitems = counters[0];
   const T cut2 = sp.re2 * (T(1) + T(1e-5));
   unsigned long long checked = 0, inrange = 0;
@@ -189,7 +247,7 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
     const int tend = min(cell_start[q + 1], t0 + kPPTargets);
     const int i0 = t0 + lane, i1 = i0 + 32;
     const bool v0 = i0 < tend, v1 = i1 < tend;
-    const V4<T> p0 = posm[v0 ? i0 : t0], p1 = posm[v1 ? i1 : t0];
+    V4<T> p0 = posm[v0 ? i0 : t0], p1 = posm[v1 ? i1 : t0];
     // bounding box of this warp's targets (code units)
     T wlo[3], whi[3];
     {
@@ -202,9 +260,16 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
       }
       wlo[0] = lx, wlo[1] = ly, wlo[2] = lz, whi[0] = hx, whi[1] = hy, whi[2] = hz;
     }
+    const int cx = (int)compact3(q), cy = (int)compact3(q >> 1), cz = (int)compact3(q >> 2);
+    // staging frame of this item
+    const T ox = TABLE ? floor(T(cx - 1) * g.hcx * T(0.25)) * T(4) : T(0);
+    const T oy = TABLE ? floor(T(cy - 1) * g.hcy * T(0.25)) * T(4) : T(0);
+    const T oz = TABLE ? floor(T(cz - 1) * g.hcz * T(0.25)) * T(4) : T(0);
+    p0.x = (p0.x - ox) * scl, p0.y = (p0.y - oy) * scl, p0.z = (p0.z - oz) * scl;
+    p1.x = (p1.x - ox) * scl, p1.y = (p1.y - oy) * scl, p1.z = (p1.z - oz) * scl;
+    auto stage = [&](V4<T> v) { return V4<T>{(v.x - ox) * scl, (v.y - oy) * scl, (v.z - oz) * scl, v.w}; };
     T a0x = 0, a0y = 0, a0z = 0, a1x = 0, a1y = 0, a1z = 0;
     unsigned n_in = 0;
-    const int cx = (int)compact3(q), cy = (int)compact3(q >> 1), cz = (int)compact3(q >> 2);
     for (int dz = -1; dz <= 1; ++dz)
       for (int dy = -1; dy <= 1; ++dy)
         for (int dx = -1; dx <= 1; ++dx) {
@@ -218,7 +283,7 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
           const V4<T>* __restrict__ sbb = own ? aabb : gaabb;
           const int s = scs[qn], e = scs[qn + 1];
           if (s >= e) continue;
-          const int box_first = s / kPPSub, box_last = (e - 1) / kPPSub;
+          const int box_first = s / SUB, box_last = (e - 1) / SUB;
           for (int b0 = box_first; b0 <= box_last; b0 += 32) {
             // exact culling, 32 boxes per ballot: a box farther than the cutoff from the targets' box
             // holds no partner of any of them
@@ -235,34 +300,36 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
             if (todo == 0u) continue;
             // software pipeline over the surviving boxes: registers hold the NEXT box while the
             // current one is consumed from shared memory
+            const V4<T> far_{T(-64), T(-64), T(-64), T(0)};  // padding: beyond the cutoff, mass 0
             int k = __ffs(todo) - 1;
             todo &= todo - 1;
-            int jb = max(s, (b0 + k) * kPPSub), je = min(e, (b0 + k + 1) * kPPSub);
-            V4<T> n0 = (jb + lane < je) ? spos[jb + lane] : V4<T>{0, 0, 0, 0};
-            V4<T> n1 = (jb + 32 + lane < je) ? spos[jb + 32 + lane] : V4<T>{0, 0, 0, 0};
+            int jb = max(s, (b0 + k) * SUB), je = min(e, (b0 + k + 1) * SUB);
+            V4<T> n0 = (jb + lane < je) ? stage(spos[jb + lane]) : far_;
+            V4<T> n1 = far_;
+            if (SUB > 32) n1 = (jb + 32 + lane < je) ? stage(spos[jb + 32 + lane]) : far_;
             for (;;) {
               const int cnt = je - jb;
               __syncwarp();
               s_src[lane] = n0;
-              s_src[lane + 32] = n1;
+              if (SUB > 32) s_src[lane + 32] = n1;
               __syncwarp();
               const bool more = todo != 0u;
               if (more) {
                 k = __ffs(todo) - 1;
                 todo &= todo - 1;
-                jb = max(s, (b0 + k) * kPPSub), je = min(e, (b0 + k + 1) * kPPSub);
-                n0 = (jb + lane < je) ? spos[jb + lane] : V4<T>{0, 0, 0, 0};
-                n1 = (jb + 32 + lane < je) ? spos[jb + 32 + lane] : V4<T>{0, 0, 0, 0};
+                jb = max(s, (b0 + k) * SUB), je = min(e, (b0 + k + 1) * SUB);
+                n0 = (jb + lane < je) ? stage(spos[jb + lane]) : far_;
+                if (SUB > 32) n1 = (jb + 32 + lane < je) ? stage(spos[jb + 32 + lane]) : far_;
               }
               if (COUNT) checked += (unsigned long long)cnt * ((v0 ? 1 : 0) + (v1 ? 1 : 0));
 #pragma unroll 8
               for (int j = 0; j < cnt; ++j) {
                 const V4<T> sj = s_src[j];
                 unsigned c0 = 0, c1 = 0;
-                pair_acc<T, TABLE, COUNT>(p0.x - sj.x, p0.y - sj.y, p0.z - sj.z, sj.w, sp, tref, a0x, a0y, a0z,
-                                          c0);
-                pair_acc<T, TABLE, COUNT>(p1.x - sj.x, p1.y - sj.y, p1.z - sj.z, sj.w, sp, tref, a1x, a1y, a1z,
-                                          c1);
+                pair_acc<T, TABLE, COUNT, UNIMASS, COPIES>(p0.x - sj.x, p0.y - sj.y, p0.z - sj.z, sj.w, sp,
+                                                           tref, a0x, a0y, a0z, c0);
+                pair_acc<T, TABLE, COUNT, UNIMASS, COPIES>(p1.x - sj.x, p1.y - sj.y, p1.z - sj.z, sj.w, sp,
+                                                           tref, a1x, a1y, a1z, c1);
                 if (COUNT) n_in += (v0 ? c0 : 0u) + (v1 ? c1 : 0u);
               }
               if (!more) break;
@@ -287,20 +354,23 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
   }
 }
 
+// Sparse cells: one thread per target walks its 27 cells straight from L1/L2 (single-copy table).
 template <typename T, bool TABLE, bool COUNT>
 __global__ void __launch_bounds__(128)
 k_pp_sparse(const V4<T>* __restrict__ posm, long long n, const int* __restrict__ cell_start,
             const V4<T>* __restrict__ gposm, const int* __restrict__ gcell_start, Geom<T> g, SRParams<T> sp, const T* __restrict__ g_tab, V4<T>* __restrict__ acc,
             V4<T>* __restrict__ acc_sr, unsigned long long* __restrict__ pair_counts) {
   __shared__ V2<T> s_tab[kSRTable];
-  __shared__ unsigned s_tb;
-  load_table(g_tab, s_tab);
-  TableRef<T> tref(s_tab, &s_tb);
+  __shared__ unsigned s_tb[32];
+  const T re = sqrt(sp.re2);
+  const T scl = TABLE ? T(1) / re : T(1);
+  load_table<T, 1>(g_tab, s_tab, TABLE ? re : T(1));
+  TableRef<T, 1> tref(s_tab, s_tb);
   __syncthreads();
-  tref.finish(&s_tb);
+  tref.finish(s_tb);
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const V4<T> p = posm[i];
+  V4<T> p = posm[i];
   int cx, cy, cz;
   bool inside;
   bin_cell(g, p.x, p.y, p.z, cx, cy, cz, inside);
@@ -322,8 +392,9 @@ k_pp_sparse(const V4<T>* __restrict__ posm, long long n, const int* __restrict__
         if (COUNT) checked += (unsigned long long)(e - s);
         for (int j = s; j < e; ++j) {
           const V4<T> sj = spos[j];
-          pair_acc<T, TABLE, COUNT>(p.x - sj.x, p.y - sj.y, p.z - sj.z, sj.w, sp, tref, ax, ay, az,
-                                    n_in);
+          // differences of code-unit coordinates are exact for close pairs (as in the reference)
+          pair_acc<T, TABLE, COUNT, false, 1>((p.x - sj.x) * scl, (p.y - sj.y) * scl, (p.z - sj.z) * scl, sj.w,
+                                              sp, tref, ax, ay, az, n_in);
         }
       }
   acc_sr[i] = V4<T>{ax, ay, az, 0};
@@ -409,7 +480,7 @@ __global__ void k_iota_zero(unsigned* idx, unsigned* cost, long long n) {
   if (i < n) idx[i] = (unsigned)i, cost[i] = 0u;
 }
 
-template <typename T, bool TABLE, bool COUNT>
+template <typename T, bool TABLE, bool COUNT, bool UNIMASS>
 static int run_pp(p3m_ctx* c) {
   State<T>& s = Sel<T>::st(c);
   const Geom<T>& g = Sel<T>::g(c);
@@ -434,9 +505,12 @@ static int run_pp(p3m_ctx* c) {
   P3M_CUDA(cub::DeviceRadixSort::SortPairsDescending(s.cub_tmp, tmp, cost, cost_sorted, idx, order,
                                                      (int)max_items, 0, 32, c->stream));
   c->launches += 5;
-  k_pp_tiled<T, TABLE, COUNT><<<c->num_sms * 8, 128, 0, c->stream>>>(
+  auto kern = k_pp_tiled<T, TABLE, COUNT, UNIMASS, kPPSub>;
+  const size_t smem = PPCfg<T>::smem(kPPSub);
+  P3M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<c->num_sms * PPCfg<T>::kCtasPerSm, PPCfg<T>::kWarps * 32, smem, c->stream>>>(
       s.posm, s.cell_start, s.aabb, s.gposm, s.gcell_start, s.gaabb, s.pp_items, order, s.pp_counters, g, sp,
-      s.sr_table, s.acc, s.acc_sr, s.pair_counts);
+      s.sr_table, (T)c->uniform_mass_code, s.acc, s.acc_sr, s.pair_counts);
   P3M_LAUNCH_CHECK(c);
   k_pp_sparse<T, TABLE, COUNT><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(
       s.posm, n, s.cell_start, s.gposm, s.gcell_start, g, sp, s.sr_table, s.acc, s.acc_sr, s.pair_counts);
@@ -452,10 +526,14 @@ int short_range(p3m_ctx* c) {
   phase_begin(c, PH_SHORT_RANGE);
   int r;
   const bool table = c->prm.use_sr_table != 0, count = c->count_pairs != 0;
-  if (table && !count) r = run_pp<T, true, false>(c);
-  else if (table && count) r = run_pp<T, true, true>(c);
-  else if (!table && !count) r = run_pp<T, false, false>(c);
-  else r = run_pp<T, false, true>(c);
+  // all masses equal (the reference's samplers: masses = M / n): the mass is folded into the table
+  const bool uni = table && c->uniform_mass;
+  if (uni && !count) r = run_pp<T, true, false, true>(c);
+  else if (uni && count) r = run_pp<T, true, true, true>(c);
+  else if (table && !count) r = run_pp<T, true, false, false>(c);
+  else if (table && count) r = run_pp<T, true, true, false>(c);
+  else if (!table && !count) r = run_pp<T, false, false, false>(c);
+  else r = run_pp<T, false, true, false>(c);
   phase_end(c, PH_SHORT_RANGE);
   return r;
 }
