@@ -92,8 +92,13 @@ int p3m_destroy(p3m_ctx* ctx);
  * to every rank by any means (bench.py: torch.distributed broadcast); all ranks then call
  * p3m_create_dist collectively.  Afterwards the SAME calls as on one GPU drive the run (they become
  * collective): p3m_set_particles takes the full particle set on every rank and keeps this rank's
- * slab; p3m_force / p3m_step migrate particles, exchange ghost layers and sum the density mesh over
- * NVLink; id-indexed readbacks fill the entries of the particles the rank holds and leave the rest 0. */
+ * slab; p3m_force / p3m_step migrate particles, exchange ghost layers, move density planes to the ranks
+ * that own them in the slab-decomposed FFT (2-D FFTs on local planes, all-to-all transpose, 1-D FFTs
+ * along z, and back) and return the potential planes each rank's particles need, all over NVLink;
+ * id-indexed readbacks fill the entries of the particles the rank holds and leave the rest 0, mesh
+ * readbacks fill the planes of the rank's FFT slab and leave the rest 0 (sum over ranks = full mesh).
+ * The mesh is slab-decomposed when nz and ny are multiples of nranks; otherwise every rank keeps a full
+ * mesh and the density is all-reduced (small meshes only). */
 #define P3M_UNIQUE_ID_BYTES 128
 int p3m_comm_unique_id(void* out_bytes128);
 int p3m_create_dist(const p3m_params* params, const void* unique_id_bytes128, int rank, int nranks,
@@ -108,8 +113,10 @@ int64_t p3m_num_global(const p3m_ctx* ctx);
 /* host-only: the binning layers along z and their cuts for `nranks` ranks (cuts[r]..cuts[r+1] belongs to
  * rank r); needs no device, identical on every rank.  layers_out = number of layers that are cut. */
 int p3m_slab_cuts(const p3m_params* params, int nranks, int32_t cuts[9], int32_t* layers_out);
-/* out = {rank, nranks, first owned binning layer, one past the last, ghost particles held} */
-int p3m_rank_info(p3m_ctx* ctx, int64_t out[5]);
+/* out = {rank, nranks, first owned binning layer, one past the last, ghost particles held,
+ *        1 if the mesh is slab-decomposed (distributed FFT) / 0 if replicated, first mesh plane of this
+ *        rank's FFT slab, number of planes in it} */
+int p3m_rank_info(p3m_ctx* ctx, int64_t out[8]);
 
 /* Particle upload.  units = P3M_UNITS_ORIGINAL applies stateToCodeUnits + massToCodeUnits on the
  * device (source/unitConversions.cpp:23-71, include/unitConversions.h:8-50), as the head of run()

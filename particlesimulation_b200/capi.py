@@ -202,9 +202,10 @@ class Context:
         return int(lib().p3m_num_global(self._h))
 
     def rank_info(self):
-        d = np.zeros(5, np.int64)
+        d = np.zeros(8, np.int64)
         _check(lib().p3m_rank_info(self._h, _p(d)))
-        return dict(zip(("rank", "nranks", "layer0", "layer1", "ghosts"), (int(v) for v in d)))
+        return dict(zip(("rank", "nranks", "layer0", "layer1", "ghosts", "slab", "plane0", "planes"),
+                        (int(v) for v in d)))
 
     def get_local(self, units=UNITS_ORIGINAL, want=("pos", "vel")):
         n = self.n

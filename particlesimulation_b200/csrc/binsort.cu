@@ -416,6 +416,7 @@ int add_acceleration(p3m_ctx* c, const float* a, int units) {
 template <typename T>
 void free_state(p3m_ctx* c) {
   State<T>& s = Sel<T>::st(c);
+  slab_free<T>(c);
   void* ptrs[] = {s.posm,   s.posm_alt,  s.vel,      s.vel_alt,  s.acc,        s.acc_sr,  s.id,
                   s.id_alt, s.keys,      s.keys_alt, s.slots,    s.slots_alt,  s.cub_tmp, s.cell_start,
                   s.density, s.potential, s.spectrum, s.green,    s.field,      s.sr_table, s.pp_items, s.aabb, s.gposm, s.gposm_alt, s.gid, s.gid_alt, s.gcell_start, s.gaabb,

@@ -106,8 +106,9 @@ static int setup_geometry(p3m_ctx* c) {
 }
 
 template <typename T>
-static int create_typed(p3m_ctx* c) {
+static int create_typed(p3m_ctx* c, const void* uid, int rank, int nranks) {
   P3M_TRY(setup_geometry<T>(c));
+  P3M_TRY(dist_init(c, uid, rank, nranks));  // cuts + communicator first: the mesh layout depends on them
   P3M_TRY(alloc_meshes<T>(c));
   if (c->prm.p3m) P3M_TRY(sr_table_upload<T>(c));
   return 0;
@@ -138,7 +139,7 @@ void p3m_default_params(p3m_params* p) {
   p->device = -1;
 }
 
-int p3m_create(const p3m_params* prm, p3m_ctx** out) {
+static int create_common(const p3m_params* prm, const void* uid, int rank, int nranks, p3m_ctx** out) {
   if (!prm || !out) return fail(P3M_EINVAL, "p3m_create: null argument");
   *out = nullptr;
   if (prm->nx < 2 || prm->ny < 2 || prm->nz < 2) return fail(P3M_EINVAL, "mesh must be at least 2^3");
@@ -193,14 +194,17 @@ int p3m_create(const p3m_params* prm, p3m_ctx** out) {
     const double dDT = DT, dH = H, dG = G, dpi = 3.14159265358979323846;
     c->mass_factor64 = dDT * dDT * 4 * dpi * dG / (dH * dH * dH);
   }
-  int r = c->f64 ? create_typed<double>(c) : create_typed<float>(c);
-  if (r == 0) r = dist_init(c, nullptr, 0, 1);  // single rank: owns every layer
+  int r = c->f64 ? create_typed<double>(c, uid, rank, nranks) : create_typed<float>(c, uid, rank, nranks);
   if (r != 0) {
     p3m_destroy(c);
     return r;
   }
   *out = c;
   return 0;
+}
+
+int p3m_create(const p3m_params* prm, p3m_ctx** out) {
+  return create_common(prm, nullptr, 0, 1, out);  // single rank: owns every layer
 }
 
 int p3m_slab_cuts(const p3m_params* prm, int nranks, int32_t cuts[9], int32_t* layers_out) {
@@ -225,16 +229,7 @@ int p3m_comm_unique_id(void* out) {
 
 int p3m_create_dist(const p3m_params* prm, const void* uid, int rank, int nranks, p3m_ctx** out) {
   if (!uid && nranks > 1) return fail(P3M_EINVAL, "p3m_create_dist: null unique id");
-  p3m_ctx* c = nullptr;
-  int r = p3m_create(prm, &c);
-  if (r != 0) return r;
-  r = dist_init(c, uid, rank, nranks);
-  if (r != 0) {
-    p3m_destroy(c);
-    return r;
-  }
-  *out = c;
-  return 0;
+  return create_common(prm, uid, rank, nranks, out);
 }
 
 int p3m_get_local(p3m_ctx* c, int32_t* ids, float* pos, float* vel, float* acc, int units) {
@@ -259,12 +254,14 @@ int p3m_set_particles_ids(p3m_ctx* c, const float* pos, const float* vel, const 
 
 int64_t p3m_num_global(const p3m_ctx* c) { return c ? (c->nranks > 1 ? c->n_global : c->n) : 0; }
 
-int p3m_rank_info(p3m_ctx* c, int64_t out[5]) {
+int p3m_rank_info(p3m_ctx* c, int64_t out[8]) {
   if (!c || !out) return fail(P3M_EINVAL, "null argument");
   out[0] = c->rank, out[1] = c->nranks;
   out[2] = c->f64 ? c->g64.cut[c->rank] : c->g32.cut[c->rank];
   out[3] = c->f64 ? c->g64.cut[c->rank + 1 > 8 ? 8 : c->rank + 1] : c->g32.cut[c->rank + 1 > 8 ? 8 : c->rank + 1];
   out[4] = c->f64 ? c->s64.n_ghost : c->s32.n_ghost;
+  const int nzl = c->prm.nz / (c->slab ? c->nranks : 1);
+  out[5] = c->slab ? 1 : 0, out[6] = c->slab ? (int64_t)c->rank * nzl : 0, out[7] = nzl;
   return 0;
 }
 
@@ -467,6 +464,7 @@ int p3m_set_potential(p3m_ctx* c, const float* m) {
   CHECK_CTX(c);
   int r = c->f64 ? set_mesh<double, float>(c, c->s64.potential, m, c->g64.M)
                  : set_mesh<float, float>(c, c->s32.potential, m, c->g32.M);
+  if (r == 0 && c->slab) r = c->f64 ? slab_spread_potential<double>(c) : slab_spread_potential<float>(c);
   if (r == 0) c->have_potential = true;
   return r;
 }

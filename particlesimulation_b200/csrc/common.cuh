@@ -74,7 +74,20 @@ struct Geom {
   int nranks, rank;
   int cut[9];
   int lay0, lay1;
+  // planes held by the buffers the particle kernels address (single GPU: the whole mesh)
+  long long den_off, den_len;  // density buffer = global flat indices [den_off, den_off + den_len)
+  int pot_z0, pot_nz;          // potential buffer = unwrapped planes [pot_z0, pot_z0 + pot_nz)
 };
+
+// plane of the local potential buffer holding (periodic) mesh plane z, or -1 if it is not held
+template <typename T>
+__device__ __forceinline__ int pot_plane(const Geom<T>& g, int z) {
+  int zl = z - g.pot_z0;
+  zl = zl < 0 ? zl + g.nz : zl;
+  zl = zl >= g.nz ? zl - g.nz : zl;
+  if (zl < 0 || zl >= g.nz) zl = ((zl % g.nz) + g.nz) % g.nz;
+  return zl < g.pot_nz ? zl : -1;
+}
 
 // owner rank of a binning-cell layer
 template <typename T>

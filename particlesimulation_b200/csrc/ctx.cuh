@@ -41,6 +41,17 @@ struct State {
   cplx* spectrum = nullptr;  // (nx/2+1)*ny*nz
   T* green = nullptr;        // (nx/2+1)*ny*nz, symmetrised, includes 1/M
   T* field = nullptr;        // 3M (only after p3m_gradient)
+  // slab-decomposed mesh (nranks > 1, dist_mesh.cu).  `density` / `potential` are then this rank's FFT
+  // slab (planes [rank*nz/P, (rank+1)*nz/P)); the particle kernels work on the planes their own z-slab
+  // of particles touches: dens_part (planes g.den_z0 ..) and pot_part (unwrapped planes g.pot_z0 ..).
+  // Single GPU: dens_part == density, pot_part == potential.
+  T* dens_part = nullptr;
+  T* pot_part = nullptr;
+  T* den_stage = nullptr;       // received density planes before they are summed into the slab
+  cplx* spectrum_t = nullptr;   // transposed half spectrum [kx, ky_local, kz]
+  cplx* pack = nullptr;         // all-to-all staging, P chunks of [kx, ky_local, z_local]
+  cufftHandle plan_z = 0;
+  bool plan_z_made = false;
   // short range
   T* sr_table = nullptr;  // 2*kSRTable: (F[t], F[t+1]-F[t]) pairs; entry 499 = (0,0)
   int* pp_items = nullptr;     // (cell, first target) pairs for the tiled kernel
@@ -88,6 +99,10 @@ struct p3m_ctx {
   void* nccl_comm = nullptr;  // ncclComm_t
   int rank = 0, nranks = 1;
   long long n_global = 0;
+  bool slab = false;          // slab-decomposed mesh + distributed FFT (else: replicated mesh, all-reduce)
+  // static plane ranges of every rank (identical on all ranks): density planes deposited by the
+  // particle slab, unwrapped potential planes its gather needs
+  int den_z0[8] = {0}, den_nz[8] = {0}, pot_z0[8] = {0}, pot_nz[8] = {0};
   int* dist_counts = nullptr;       // device: nranks + 1 segment starts, then nranks*nranks counts, then 4 ghost counts * nranks
   int* dist_counts_host = nullptr;  // pinned mirror
 };
@@ -158,6 +173,13 @@ void dist_destroy(p3m_ctx* c);
 template <typename T> int dist_migrate(p3m_ctx* c, bool exchange);
 template <typename T> int dist_ghosts(p3m_ctx* c);
 template <typename T> int dist_allreduce_density(p3m_ctx* c);
+// dist_mesh.cu: slab-decomposed mesh
+template <typename T> int slab_setup(p3m_ctx* c);             // after dist_init: plane ranges, buffers, plans
+template <typename T> void slab_free(p3m_ctx* c);
+template <typename T> int slab_reduce_density(p3m_ctx* c);    // dens_part of all ranks -> density slabs
+template <typename T> int slab_poisson(p3m_ctx* c);           // distributed FFT Poisson solve
+template <typename T> int slab_spread_potential(p3m_ctx* c);  // potential slabs -> pot_part of all ranks
+
 int dist_allreduce(p3m_ctx* c, void* buf, size_t count, int kind /*0 int max, 1 double sum*/);
 int dist_allreduce_host_imax(p3m_ctx* c, int* v, int count /* <= 8 */);
 template <typename T> int upload_particles_ids(p3m_ctx* c, const float* pos, const float* vel, const float* mass, const int32_t* ids, long long n, int units);

@@ -36,7 +36,11 @@ __device__ __forceinline__ void deposit_direct(const Stencil<T, K>& s, const Geo
         // Grid::getIndx, unwrapped (include/grid.h:52-54)
         long long flat = (long long)(s.x0 + a) + (long long)(s.y0 + b) * g.nx +
                          (long long)(s.z0 + cc) * g.nx * g.ny;
-        if (flat >= 0 && flat < g.M) atomicAdd(&density[flat], t3);
+        // (multi-GPU: `density` holds the planes of this rank's particle slab only)
+        if (flat >= 0 && flat < g.M) {
+          flat -= g.den_off;
+          if (flat >= 0 && flat < g.den_len) atomicAdd(&density[flat], t3);
+        }
       }
     }
   }
@@ -172,7 +176,10 @@ k_deposit(const V4<T>* __restrict__ posm, long long n, int chunk, const int* __r
         const int iy = q - iz * ext[1];
         long long flat = (long long)(lo[0] + ix) + (long long)(lo[1] + iy) * g.nx +
                          (long long)(lo[2] + iz) * g.nx * g.ny;
-        if (flat >= 0 && flat < g.M) atomicAdd(&density[flat], v);
+        if (flat >= 0 && flat < g.M) {
+          flat -= g.den_off;
+          if (flat >= 0 && flat < g.den_len) atomicAdd(&density[flat], v);
+        }
       }
     }
     __syncwarp();
@@ -196,7 +203,7 @@ static int launch_deposit(p3m_ctx* c) {
   auto kern = k_deposit<T, K>;
   P3M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, smem, c->stream>>>(s.posm, n, chunk,
-                                                                         s.cell_start, g, s.density);
+                                                                         s.cell_start, g, s.dens_part);
   P3M_LAUNCH_CHECK(c);
   return 0;
 }
@@ -209,7 +216,7 @@ int deposit(p3m_ctx* c) {
   const Geom<T>& g = Sel<T>::g(c);
   phase_begin(c, PH_DEPOSIT);
   // Grid::clearDensity (source/grid.cpp:34-36)
-  P3M_CUDA(cudaMemsetAsync(s.density, 0, sizeof(T) * (size_t)g.M, c->stream));
+  P3M_CUDA(cudaMemsetAsync(s.dens_part, 0, sizeof(T) * (size_t)g.den_len, c->stream));
   c->launches++;
   int r = 0;
   if (c->n > 0) {
@@ -221,7 +228,9 @@ int deposit(p3m_ctx* c) {
       r = launch_deposit<T, 1>(c);
   }
   phase_end(c, PH_DEPOSIT);
-  if (r == 0 && c->nranks > 1) r = dist_allreduce_density<T>(c);  // sum the slabs' contributions
+  // multi-GPU: planes go to the ranks that own them in the FFT slab decomposition (or, replicated-mesh
+  // fallback, one all-reduce of the full mesh)
+  if (r == 0 && c->nranks > 1) r = c->slab ? slab_reduce_density<T>(c) : dist_allreduce_density<T>(c);
   c->have_density = (r == 0);
   return r;
 }

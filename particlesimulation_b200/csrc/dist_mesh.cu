@@ -1,0 +1,335 @@
+// dist_mesh.cu -- multi-GPU: the slab-decomposed mesh and the distributed FFT Poisson solve
+// (nothing of this exists in the reference, which is single-process).
+//
+// FFT decomposition: rank r owns the mesh planes z in [r*nz/P, (r+1)*nz/P) of density and potential.
+// The particle decomposition (dist.cu) cuts binning-cell layers, and particles only occupy the lower
+// part of the mesh (box = half the mesh per axis in the reference's set-ups), so the planes a rank's
+// particles touch are NOT the planes it owns.  Everything below is derived from the static layer cuts,
+// identically on every rank, so no sizes are ever negotiated at run time:
+//
+//   deposit     -> dens_part : planes [den_z0, den_z0 + den_nz) touched by this rank's particles
+//   slab_reduce_density     : every overlap (source planes x owner's FFT planes) travels with one grouped
+//                             ncclSend/ncclRecv and is summed into the owner's slab (fixed order -> the
+//                             result does not depend on arrival order)
+//   slab_poisson            : batched 2-D R2C over the local planes -> pack -> all-to-all (grouped
+//                             ncclSend/ncclRecv over NVLink) -> strided 1-D C2C along z on [kx, ky_local, kz]
+//                             -> multiply by the locally stored share of the influence function ->
+//                             inverse 1-D -> all-to-all back -> unpack -> batched 2-D C2R
+//   slab_spread_potential   : the unwrapped planes [pot_z0, pot_z0 + pot_nz) every rank's gather needs
+//                             (assignment stencil + finite-difference halo, periodic in z) are sent from
+//                             their owners straight into pot_part
+//
+// Per GPU and solve the all-to-all moves 2 x 8 B x (nx/2+1) x ny x nz / P x (P-1)/P bytes; mesh memory is
+// M/P per array, so a 1024^3 mesh on 8 GPUs holds 512 MiB per real slab.
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "ctx.cuh"
+
+namespace p3m {
+
+#define P3M_NCCL(expr)                                                                        \
+  do {                                                                                        \
+    ncclResult_t r__ = (expr);                                                                \
+    if (r__ != ncclSuccess)                                                                   \
+      return ::p3m::fail(P3M_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,              \
+                         ncclGetErrorString(r__));                                            \
+  } while (0)
+
+namespace {
+
+template <typename T>
+ncclDataType_t nccl_real() { return sizeof(T) == 8 ? ncclDouble : ncclFloat; }
+
+// [kx, ky, zl] -> P chunks [kx, ky_local, zl]   (forward) or back (inverse)
+template <typename C, bool PACK>
+__global__ void k_transpose_pack(C* __restrict__ planes, C* __restrict__ chunks, int nxh, int ny, int nyl,
+                                 int nzl) {
+  const long long total = (long long)nxh * ny * nzl;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int kx = (int)(i % nxh);
+    const long long q = i / nxh;
+    const int ky = (int)(q % ny), zl = (int)(q / ny);
+    const int d = ky / nyl, kyl = ky - d * nyl;
+    const long long j = (long long)d * nxh * nyl * nzl + kx + (long long)nxh * (kyl + (long long)nyl * zl);
+    if (PACK) chunks[j] = planes[i]; else planes[i] = chunks[j];
+  }
+}
+
+template <typename C, typename T>
+__global__ void k_multiply_t(C* __restrict__ spec, const T* __restrict__ table, long long count) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    C v = spec[i];
+    const T g = table[i];
+    v.x *= g, v.y *= g;
+    spec[i] = v;
+  }
+}
+
+template <typename T>
+__global__ void k_add_planes(T* __restrict__ dst, const T* __restrict__ src, long long count) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] += src[i];
+}
+
+inline cufftResult exec_r2c(cufftHandle p, float* in, cufftComplex* out) { return cufftExecR2C(p, in, out); }
+inline cufftResult exec_r2c(cufftHandle p, double* in, cufftDoubleComplex* out) { return cufftExecD2Z(p, in, out); }
+inline cufftResult exec_c2r(cufftHandle p, cufftComplex* in, float* out) { return cufftExecC2R(p, in, out); }
+inline cufftResult exec_c2r(cufftHandle p, cufftDoubleComplex* in, double* out) { return cufftExecZ2D(p, in, out); }
+inline cufftResult exec_c2c(cufftHandle p, cufftComplex* d, int dir) { return cufftExecC2C(p, d, d, dir); }
+inline cufftResult exec_c2c(cufftHandle p, cufftDoubleComplex* d, int dir) { return cufftExecZ2Z(p, d, d, dir); }
+
+inline int grid_for(long long count, int sms) {
+  long long b = (count + 255) / 256;
+  const long long cap = (long long)sms * 16;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace
+
+// ---- static plane ranges -------------------------------------------------------------------------------------
+template <typename T>
+static void plane_ranges(p3m_ctx* c) {
+  const Geom<T>& g = Sel<T>::g(c);
+  const int P = c->nranks;
+  const int FD = g.fds == P3M_TWO_POINT ? 1 : 2;
+  // z extent of the binning layers in mesh cells
+  const double hz = g.p3m ? (double)g.hcz : (double)(1 << g.tile_shift);
+  const int layers = g.cut[P];
+  int top = (int)std::ceil(layers * hz) + (g.p3m ? 2 : (1 << g.tile_shift));
+  if (top > g.nz) top = g.nz;
+  for (int r = 0; r < P; ++r) {
+    int zlo = r == 0 ? 0 : (int)std::floor(g.cut[r] * hz);
+    int zhi = r == P - 1 ? top : (int)std::ceil(g.cut[r + 1] * hz) + 1;  // +1: rounding slop of pos / HC
+    if (r > 0) zlo -= 1;
+    zlo = std::max(zlo, 0), zhi = std::min(zhi, g.nz);
+    // density: base cell in [zlo, zhi), stencil reaches one plane further on each side
+    const int d0 = std::max(zlo - 1, 0), d1 = std::min(zhi + 1, g.nz);
+    c->den_z0[r] = d0, c->den_nz[r] = d1 - d0;
+    // potential: field planes zlo-1 .. zhi, each differencing +-FD planes, periodic -> unwrapped range
+    int p0 = zlo - 1 - FD, p1 = zhi + 1 + FD;
+    if (p1 - p0 >= g.nz) p0 = 0, p1 = g.nz;
+    c->pot_z0[r] = p0, c->pot_nz[r] = p1 - p0;
+  }
+}
+
+template <typename T>
+void slab_free(p3m_ctx* c) {
+  State<T>& s = Sel<T>::st(c);
+  if (!c->slab) return;
+  void* ptrs[] = {s.dens_part, s.pot_part, s.den_stage, s.spectrum_t, s.pack};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  s.dens_part = s.pot_part = s.den_stage = nullptr;
+  s.spectrum_t = s.pack = nullptr;
+  if (s.plan_z_made) cufftDestroy(s.plan_z);
+  s.plan_z_made = false;
+}
+
+// Allocates the slab-sized meshes and the three cuFFT plans.  Called instead of the full-mesh allocation.
+template <typename T>
+int slab_setup(p3m_ctx* c) {
+  using cplx = typename State<T>::cplx;
+  State<T>& s = Sel<T>::st(c);
+  Geom<T>& g = Sel<T>::g(c);
+  const int P = c->nranks, me = c->rank;
+  const int nxh = g.nx / 2 + 1, nyl = g.ny / P, nzl = g.nz / P;
+  const size_t plane = (size_t)g.nx * g.ny;
+  plane_ranges<T>(c);
+  g.den_off = (long long)c->den_z0[me] * (long long)plane;
+  g.den_len = (long long)c->den_nz[me] * (long long)plane;
+  g.pot_z0 = c->pot_z0[me], g.pot_nz = c->pot_nz[me];
+  const size_t spec = (size_t)nxh * g.ny * nzl;  // == nxh * nyl * nz
+  P3M_CUDA(cudaMalloc((void**)&s.density, sizeof(T) * plane * nzl));
+  P3M_CUDA(cudaMalloc((void**)&s.potential, sizeof(T) * plane * nzl));
+  P3M_CUDA(cudaMalloc((void**)&s.dens_part, sizeof(T) * plane * (size_t)c->den_nz[me]));
+  P3M_CUDA(cudaMalloc((void**)&s.pot_part, sizeof(T) * plane * (size_t)c->pot_nz[me]));
+  // received density planes: every source overlaps my slab with at most nzl planes, all sources together
+  // with at most nzl + 4 planes each side of a cut
+  P3M_CUDA(cudaMalloc((void**)&s.den_stage, sizeof(T) * plane * (size_t)(nzl + 4 * P)));
+  P3M_CUDA(cudaMalloc((void**)&s.spectrum, sizeof(cplx) * spec));
+  P3M_CUDA(cudaMalloc((void**)&s.spectrum_t, sizeof(cplx) * spec));
+  P3M_CUDA(cudaMalloc((void**)&s.pack, sizeof(cplx) * spec));
+  P3M_CUDA(cudaMalloc((void**)&s.green, sizeof(T) * spec));
+  P3M_CUDA(cudaMemsetAsync(s.density, 0, sizeof(T) * plane * nzl, c->stream));
+  P3M_CUDA(cudaMemsetAsync(s.potential, 0, sizeof(T) * plane * nzl, c->stream));
+  P3M_CUDA(cudaMemsetAsync(s.pot_part, 0, sizeof(T) * plane * (size_t)c->pot_nz[me], c->stream));
+  const bool dbl = sizeof(T) == 8;
+  int n2[2] = {g.ny, g.nx};
+  P3M_FFT(cufftPlanMany(&s.plan_fwd, 2, n2, nullptr, 1, 0, nullptr, 1, 0, dbl ? CUFFT_D2Z : CUFFT_R2C, nzl));
+  P3M_FFT(cufftPlanMany(&s.plan_inv, 2, n2, nullptr, 1, 0, nullptr, 1, 0, dbl ? CUFFT_Z2D : CUFFT_C2R, nzl));
+  s.plans = true;
+  int n1[1] = {g.nz};
+  int embed[1] = {g.nz};
+  const int stride = nxh * nyl;
+  P3M_FFT(cufftPlanMany(&s.plan_z, 1, n1, embed, stride, 1, embed, stride, 1, dbl ? CUFFT_Z2Z : CUFFT_C2C, stride));
+  s.plan_z_made = true;
+  P3M_FFT(cufftSetStream(s.plan_fwd, c->stream));
+  P3M_FFT(cufftSetStream(s.plan_inv, c->stream));
+  P3M_FFT(cufftSetStream(s.plan_z, c->stream));
+  return 0;
+}
+
+// ---- density: particle slabs -> FFT slabs -----------------------------------------------------------------------
+template <typename T>
+int slab_reduce_density(p3m_ctx* c) {
+  State<T>& s = Sel<T>::st(c);
+  const Geom<T>& g = Sel<T>::g(c);
+  const int P = c->nranks, me = c->rank, nzl = g.nz / P;
+  const size_t plane = (size_t)g.nx * g.ny;
+  ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+  phase_begin(c, PH_COMM);
+  auto overlap = [&](int src, int dst, int& lo, int& hi) {
+    lo = std::max(c->den_z0[src], dst * nzl);
+    hi = std::min(c->den_z0[src] + c->den_nz[src], (dst + 1) * nzl);
+    return hi > lo;
+  };
+  P3M_CUDA(cudaMemsetAsync(s.density, 0, sizeof(T) * plane * nzl, c->stream));
+  size_t stage_off[8] = {0};
+  size_t off = 0;
+  P3M_NCCL(ncclGroupStart());
+  for (int p = 0; p < P; ++p) {
+    if (p == me) continue;
+    int lo, hi;
+    if (overlap(me, p, lo, hi))
+      P3M_NCCL(ncclSend(s.dens_part + (size_t)(lo - c->den_z0[me]) * plane, (size_t)(hi - lo) * plane, nccl_real<T>(), p,
+                        comm, c->stream));
+    if (overlap(p, me, lo, hi)) {
+      stage_off[p] = off;
+      P3M_NCCL(ncclRecv(s.den_stage + off, (size_t)(hi - lo) * plane, nccl_real<T>(), p, comm, c->stream));
+      off += (size_t)(hi - lo) * plane;
+    }
+  }
+  P3M_NCCL(ncclGroupEnd());
+  c->launches++;
+  // sum in rank order: bit-reproducible
+  for (int p = 0; p < P; ++p) {
+    int lo, hi;
+    if (!overlap(p, me, lo, hi)) continue;
+    const T* src = p == me ? s.dens_part + (size_t)(lo - c->den_z0[me]) * plane : s.den_stage + stage_off[p];
+    const long long cnt = (long long)(hi - lo) * (long long)plane;
+    k_add_planes<T><<<grid_for(cnt, c->num_sms), 256, 0, c->stream>>>(s.density + (size_t)(lo - me * nzl) * plane, src, cnt);
+    P3M_LAUNCH_CHECK(c);
+  }
+  phase_end(c, PH_COMM);
+  return 0;
+}
+
+// ---- potential: FFT slabs -> particle slabs (unwrapped, with halo) ------------------------------------------------
+template <typename T>
+int slab_spread_potential(p3m_ctx* c) {
+  State<T>& s = Sel<T>::st(c);
+  const Geom<T>& g = Sel<T>::g(c);
+  const int P = c->nranks, me = c->rank, nzl = g.nz / P;
+  const size_t plane = (size_t)g.nx * g.ny;
+  ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+  phase_begin(c, PH_COMM);
+  // planes of owner `own`, periodic image k, wanted by particle rank `dst`: unwrapped [lo, hi)
+  auto overlap = [&](int own, int k, int dst, int& lo, int& hi) {
+    lo = std::max(own * nzl + k * g.nz, c->pot_z0[dst]);
+    hi = std::min((own + 1) * nzl + k * g.nz, c->pot_z0[dst] + c->pot_nz[dst]);
+    return hi > lo;
+  };
+  P3M_NCCL(ncclGroupStart());
+  for (int p = 0; p < P; ++p)
+    for (int k = -1; k <= 1; ++k) {
+      int lo, hi;
+      if (p != me && overlap(me, k, p, lo, hi))
+        P3M_NCCL(ncclSend(s.potential + (size_t)(lo - k * g.nz - me * nzl) * plane, (size_t)(hi - lo) * plane,
+                          nccl_real<T>(), p, comm, c->stream));
+      if (p != me && overlap(p, k, me, lo, hi))
+        P3M_NCCL(ncclRecv(s.pot_part + (size_t)(lo - c->pot_z0[me]) * plane, (size_t)(hi - lo) * plane, nccl_real<T>(),
+                          p, comm, c->stream));
+    }
+  P3M_NCCL(ncclGroupEnd());
+  c->launches++;
+  for (int k = -1; k <= 1; ++k) {
+    int lo, hi;
+    if (overlap(me, k, me, lo, hi))
+      P3M_CUDA(cudaMemcpyAsync(s.pot_part + (size_t)(lo - c->pot_z0[me]) * plane,
+                               s.potential + (size_t)(lo - k * g.nz - me * nzl) * plane, sizeof(T) * (size_t)(hi - lo) * plane,
+                               cudaMemcpyDeviceToDevice, c->stream));
+  }
+  phase_end(c, PH_COMM);
+  return 0;
+}
+
+// ---- the distributed Poisson solve ----------------------------------------------------------------------------------
+template <typename T>
+static int all_to_all(p3m_ctx* c, typename State<T>::cplx* send, typename State<T>::cplx* recv, size_t chunk) {
+  using cplx = typename State<T>::cplx;
+  const int P = c->nranks, me = c->rank;
+  ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+  P3M_NCCL(ncclGroupStart());
+  for (int p = 0; p < P; ++p) {
+    if (p == me) continue;
+    P3M_NCCL(ncclSend(send + (size_t)p * chunk, chunk * sizeof(cplx), ncclChar, p, comm, c->stream));
+    P3M_NCCL(ncclRecv(recv + (size_t)p * chunk, chunk * sizeof(cplx), ncclChar, p, comm, c->stream));
+  }
+  P3M_NCCL(ncclGroupEnd());
+  P3M_CUDA(cudaMemcpyAsync(recv + (size_t)me * chunk, send + (size_t)me * chunk, chunk * sizeof(cplx),
+                           cudaMemcpyDeviceToDevice, c->stream));
+  c->launches += 2;
+  return 0;
+}
+
+template <typename T>
+int slab_poisson(p3m_ctx* c) {
+  using cplx = typename State<T>::cplx;
+  State<T>& s = Sel<T>::st(c);
+  const Geom<T>& g = Sel<T>::g(c);
+  const int P = c->nranks;
+  const int nxh = g.nx / 2 + 1, nyl = g.ny / P, nzl = g.nz / P;
+  const long long spec = (long long)nxh * g.ny * nzl;
+  const size_t chunk = (size_t)nxh * nyl * nzl;
+  const int grid = grid_for(spec, c->num_sms);
+  phase_begin(c, PH_FFT_FWD);
+  P3M_FFT(exec_r2c(s.plan_fwd, s.density, s.spectrum));
+  k_transpose_pack<cplx, true><<<grid, 256, 0, c->stream>>>(s.spectrum, s.pack, nxh, g.ny, nyl, nzl);
+  P3M_LAUNCH_CHECK(c);
+  c->launches += 2;
+  phase_end(c, PH_FFT_FWD);
+  phase_begin(c, PH_COMM);
+  P3M_TRY(all_to_all<T>(c, s.pack, s.spectrum_t, chunk));  // chunk p = planes of rank p: [kx, ky_local, z]
+  phase_end(c, PH_COMM);
+  phase_begin(c, PH_FFT_FWD);
+  P3M_FFT(exec_c2c(s.plan_z, s.spectrum_t, CUFFT_FORWARD));
+  c->launches++;
+  phase_end(c, PH_FFT_FWD);
+  phase_begin(c, PH_MULTIPLY);
+  k_multiply_t<<<grid, 256, 0, c->stream>>>(s.spectrum_t, s.green, spec);
+  P3M_LAUNCH_CHECK(c);
+  phase_end(c, PH_MULTIPLY);
+  phase_begin(c, PH_FFT_INV);
+  P3M_FFT(exec_c2c(s.plan_z, s.spectrum_t, CUFFT_INVERSE));
+  c->launches++;
+  phase_end(c, PH_FFT_INV);
+  phase_begin(c, PH_COMM);
+  P3M_TRY(all_to_all<T>(c, s.spectrum_t, s.pack, chunk));  // chunk p of the transposed array = planes of rank p
+  phase_end(c, PH_COMM);
+  phase_begin(c, PH_FFT_INV);
+  k_transpose_pack<cplx, false><<<grid, 256, 0, c->stream>>>(s.spectrum, s.pack, nxh, g.ny, nyl, nzl);
+  P3M_LAUNCH_CHECK(c);
+  P3M_FFT(exec_c2r(s.plan_inv, s.spectrum, s.potential));
+  c->launches += 2;
+  phase_end(c, PH_FFT_INV);
+  return 0;
+}
+
+template void slab_free<float>(p3m_ctx*);
+template void slab_free<double>(p3m_ctx*);
+template int slab_setup<float>(p3m_ctx*);
+template int slab_setup<double>(p3m_ctx*);
+template int slab_reduce_density<float>(p3m_ctx*);
+template int slab_reduce_density<double>(p3m_ctx*);
+template int slab_spread_potential<float>(p3m_ctx*);
+template int slab_spread_potential<double>(p3m_ctx*);
+template int slab_poisson<float>(p3m_ctx*);
+template int slab_poisson<double>(p3m_ctx*);
+
+}  // namespace p3m

@@ -23,7 +23,8 @@ __device__ __forceinline__ void field_at(const T* __restrict__ phi, const Geom<T
                                          int z, T& fx, T& fy, T& fz) {
   const long long sx = 1, sy = g.nx, sz = (long long)g.nx * g.ny;
   auto P = [&](int a, int b, int cc) -> T {
-    return phi[wrap_idx(a, g.nx) * sx + wrap_idx(b, g.ny) * sy + wrap_idx(cc, g.nz) * sz];
+    const int zl = pot_plane(g, cc);  // multi-GPU: `phi` holds the planes of this rank's particle slab
+    return zl < 0 ? T(0) : phi[wrap_idx(a, g.nx) * sx + wrap_idx(b, g.ny) * sy + zl * sz];
   };
   if (FD == 1) {
     fx = T(-0.5) * (P(x + 1, y, z) - P(x - 1, y, z));
@@ -129,8 +130,8 @@ k_gather(const V4<T>* __restrict__ posm, long long n, int chunk, const int* __re
         const int iz = fast_div(q, py, ipy);
         const int iy = q - iz * py;
         const int gx = wrap_idx(lo[0] - FD + ix, g.nx), gy = wrap_idx(lo[1] - FD + iy, g.ny),
-                  gz = wrap_idx(lo[2] - FD + iz, g.nz);
-        sphi[e] = phi[(long long)gx + (long long)gy * g.nx + (long long)gz * g.nx * g.ny];
+                  gz = pot_plane(g, lo[2] - FD + iz);
+        sphi[e] = gz < 0 ? T(0) : phi[(long long)gx + (long long)gy * g.nx + (long long)gz * g.nx * g.ny];
       }
     }
     __syncthreads();
@@ -204,7 +205,7 @@ static int launch_gather(p3m_ctx* c) {
                                    4 * (size_t)g.tex * g.tey * g.tez);
   auto kern = k_gather<T, K, FD>;
   P3M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)blocks, 256, smem, c->stream>>>(s.posm, n, chunk, s.cell_start, g, s.potential,
+  kern<<<(unsigned)blocks, 256, smem, c->stream>>>(s.posm, n, chunk, s.cell_start, g, s.pot_part,
                                                    s.acc);
   P3M_LAUNCH_CHECK(c);
   return 0;
@@ -246,6 +247,7 @@ __global__ void k_gradient(const T* __restrict__ phi, Geom<T> g, T* __restrict__
 template <typename T>
 int gradient(p3m_ctx* c) {
   if (!c->have_potential) return fail(P3M_ESTATE, "p3m_gradient: no potential (call p3m_poisson)");
+  if (c->slab) return fail(P3M_ESTATE, "p3m_gradient: the explicit field mesh is not built on a slab-decomposed mesh");
   State<T>& s = Sel<T>::st(c);
   const Geom<T>& g = Sel<T>::g(c);
   if (!s.field) P3M_CUDA(cudaMalloc((void**)&s.field, sizeof(T) * 3 * (size_t)g.M));

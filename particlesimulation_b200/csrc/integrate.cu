@@ -185,8 +185,10 @@ int diagnostics(p3m_ctx* c, double* out) {
   }
   if (c->have_density && c->have_potential) {
     // the mesh is replicated on every rank: each sums its share of the cells
+    // (slab-decomposed mesh: density / potential ARE this rank's planes)
     const long long share = (g.M + c->nranks - 1) / c->nranks;
-    const long long first = share * c->rank, last = first + share < g.M ? first + share : g.M;
+    const long long first = c->slab ? 0 : share * c->rank;
+    const long long last = c->slab ? g.M / c->nranks : (first + share < g.M ? first + share : g.M);
     k_diag_mesh<T><<<blocks, 256, 0, c->stream>>>(s.density, s.potential, first, last, s.diag);
     P3M_LAUNCH_CHECK(c);
   }

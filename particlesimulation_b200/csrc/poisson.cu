@@ -16,6 +16,8 @@
 // real operator G_sym(k) = (G(k) + G(-k mod N)) / 2.  The table stored here is G_sym / M.
 //
 // The table is always EVALUATED in fp64 (once per run) and rounded to the mesh precision.
+#include <cstdlib>
+
 #include "ctx.cuh"
 
 namespace p3m {
@@ -148,6 +150,32 @@ __global__ void k_green_to_full(const T* __restrict__ table, int nx, int ny, int
   full[idx] = (double)table[kx + (long long)ky * nxh + (long long)kz * nxh * ny] * (double)M;
 }
 
+// slab-decomposed mesh: this rank's share of the table in the transposed layout [kx, ky_local, kz]
+template <typename T>
+__global__ void k_green_slab(GreenCfg c, int ky0, int nyl, long long count, T* __restrict__ table) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= count) return;
+  const int nxh = c.nx / 2 + 1;
+  const int kx = (int)(idx % nxh), ky = ky0 + (int)((idx / nxh) % nyl), kz = (int)(idx / ((long long)nxh * nyl));
+  const double g1 = green_value(c, kx, ky, kz);
+  const double g2 = green_value(c, (c.nx - kx) % c.nx, (c.ny - ky) % c.ny, (c.nz - kz) % c.nz);
+  const double M = (double)c.nx * c.ny * c.nz;
+  table[idx] = (T)(0.5 * (g1 + g2) / M);
+}
+
+template <typename T, typename I>
+__global__ void k_green_slab_from_full(const I* __restrict__ full, int nx, int ny, int nz, int ky0, int nyl,
+                                       long long count, T* __restrict__ table) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= count) return;
+  const int nxh = nx / 2 + 1;
+  const int kx = (int)(idx % nxh), ky = ky0 + (int)((idx / nxh) % nyl), kz = (int)(idx / ((long long)nxh * nyl));
+  const long long a = kx + (long long)ky * nx + (long long)kz * nx * ny;
+  const long long b = (nx - kx) % nx + (long long)((ny - ky) % ny) * nx + (long long)((nz - kz) % nz) * nx * ny;
+  const double M = (double)nx * ny * nz;
+  table[idx] = (T)(0.5 * ((double)full[a] + (double)full[b]) / M);
+}
+
 template <typename C, typename T>
 __global__ void k_multiply(C* __restrict__ spec, const T* __restrict__ table, long long count) {
   long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -172,7 +200,13 @@ int green_init(p3m_ctx* c) {
                (double)p.particle_diameter / (double)p.H, p.green_zero_degenerate};
   if (!c->f64) cfg.a = (double)(p.particle_diameter / p.H);  // lengthToCodeUnits in fp32 (:56)
   const long long hc = half_count(p);
-  k_green<T><<<(unsigned)((hc + 127) / 128), 128, 0, c->stream>>>(cfg, hc, s.green);
+  if (c->slab) {
+    const int nyl = p.ny / c->nranks;
+    const long long cnt = hc / c->nranks;
+    k_green_slab<T><<<(unsigned)((cnt + 127) / 128), 128, 0, c->stream>>>(cfg, c->rank * nyl, nyl, cnt, s.green);
+  } else {
+    k_green<T><<<(unsigned)((hc + 127) / 128), 128, 0, c->stream>>>(cfg, hc, s.green);
+  }
   P3M_LAUNCH_CHECK(c);
   c->have_green = true;
   return 0;
@@ -186,8 +220,15 @@ int green_set(p3m_ctx* c, const I* full) {
   I* stage = nullptr;
   P3M_CUDA(cudaMallocAsync((void**)&stage, sizeof(I) * (size_t)M, c->stream));
   P3M_CUDA(cudaMemcpyAsync(stage, full, sizeof(I) * (size_t)M, cudaMemcpyHostToDevice, c->stream));
-  k_green_from_full<T, I><<<(unsigned)((hc + 255) / 256), 256, 0, c->stream>>>(stage, p.nx, p.ny, p.nz,
-                                                                             hc, s.green);
+  if (c->slab) {
+    const int nyl = p.ny / c->nranks;
+    const long long cnt = hc / c->nranks;
+    k_green_slab_from_full<T, I><<<(unsigned)((cnt + 255) / 256), 256, 0, c->stream>>>(
+        stage, p.nx, p.ny, p.nz, c->rank * nyl, nyl, cnt, s.green);
+  } else {
+    k_green_from_full<T, I><<<(unsigned)((hc + 255) / 256), 256, 0, c->stream>>>(stage, p.nx, p.ny, p.nz,
+                                                                               hc, s.green);
+  }
   P3M_LAUNCH_CHECK(c);
   P3M_CUDA(cudaFreeAsync(stage, c->stream));
   P3M_CUDA(cudaStreamSynchronize(c->stream));
@@ -198,6 +239,7 @@ int green_set(p3m_ctx* c, const I* full) {
 template <typename T>
 int green_get(p3m_ctx* c, double* full) {
   if (!c->have_green) return fail(P3M_ESTATE, "p3m_get_green_table: table not initialised");
+  if (c->slab) return fail(P3M_ESTATE, "p3m_get_green_table: the table is distributed (slab-decomposed mesh)");
   State<T>& s = Sel<T>::st(c);
   const p3m_params& p = c->prm;
   const long long M = (long long)p.nx * p.ny * p.nz;
@@ -219,13 +261,30 @@ static cufftResult exec_inv(cufftHandle p, cufftDoubleComplex* in, double* out) 
 template <typename T>
 int alloc_meshes(p3m_ctx* c) {
   State<T>& s = Sel<T>::st(c);
-  const Geom<T>& g = Sel<T>::g(c);
+  Geom<T>& g = Sel<T>::g(c);
   const p3m_params& p = c->prm;
   const long long hc = half_count(p);
-  P3M_CUDA(cudaMalloc((void**)&s.density, sizeof(T) * (size_t)g.M));
-  P3M_CUDA(cudaMalloc((void**)&s.potential, sizeof(T) * (size_t)g.M));
-  P3M_CUDA(cudaMalloc((void**)&s.spectrum, sizeof(typename State<T>::cplx) * (size_t)hc));
-  P3M_CUDA(cudaMalloc((void**)&s.green, sizeof(T) * (size_t)hc));
+  // several ranks: slab-decomposed mesh whenever the planes and the ky rows divide evenly
+  c->slab = c->nranks > 1 && p.nz % c->nranks == 0 && p.ny % c->nranks == 0 && !getenv("P3M_REPLICATED_MESH");
+  if (c->slab) {
+    P3M_TRY(slab_setup<T>(c));
+  } else {
+    P3M_CUDA(cudaMalloc((void**)&s.density, sizeof(T) * (size_t)g.M));
+    P3M_CUDA(cudaMalloc((void**)&s.potential, sizeof(T) * (size_t)g.M));
+    P3M_CUDA(cudaMalloc((void**)&s.spectrum, sizeof(typename State<T>::cplx) * (size_t)hc));
+    P3M_CUDA(cudaMalloc((void**)&s.green, sizeof(T) * (size_t)hc));
+    s.dens_part = s.density, s.pot_part = s.potential;
+    g.den_off = 0, g.den_len = g.M, g.pot_z0 = 0, g.pot_nz = g.nz;
+    P3M_CUDA(cudaMemsetAsync(s.density, 0, sizeof(T) * (size_t)g.M, c->stream));
+    P3M_CUDA(cudaMemsetAsync(s.potential, 0, sizeof(T) * (size_t)g.M, c->stream));
+    const bool dbl = sizeof(T) == 8;
+    // adapters get dims {Nz, Ny, Nx} (source/demos.cpp:758-759): x is the fastest axis
+    P3M_FFT(cufftPlan3d(&s.plan_fwd, p.nz, p.ny, p.nx, dbl ? CUFFT_D2Z : CUFFT_R2C));
+    P3M_FFT(cufftPlan3d(&s.plan_inv, p.nz, p.ny, p.nx, dbl ? CUFFT_Z2D : CUFFT_C2R));
+    s.plans = true;
+    P3M_FFT(cufftSetStream(s.plan_fwd, c->stream));
+    P3M_FFT(cufftSetStream(s.plan_inv, c->stream));
+  }
   P3M_CUDA(cudaMalloc((void**)&s.cell_start, sizeof(int) * (((size_t)1 << (3 * g.mbits)) + 2)));
   P3M_CUDA(cudaMalloc((void**)&s.sr_table, sizeof(T) * 2 * kSRTable));
   P3M_CUDA(cudaMalloc((void**)&s.pp_counters, sizeof(int) * 8));
@@ -234,15 +293,6 @@ int alloc_meshes(p3m_ctx* c) {
   P3M_CUDA(cudaMalloc((void**)&s.diag, sizeof(double) * 16));
   P3M_CUDA(cudaMemsetAsync(s.flags, 0, sizeof(int) * 4, c->stream));
   P3M_CUDA(cudaMemsetAsync(s.pair_counts, 0, sizeof(unsigned long long) * 2, c->stream));
-  P3M_CUDA(cudaMemsetAsync(s.density, 0, sizeof(T) * (size_t)g.M, c->stream));
-  P3M_CUDA(cudaMemsetAsync(s.potential, 0, sizeof(T) * (size_t)g.M, c->stream));
-  const bool dbl = sizeof(T) == 8;
-  // adapters get dims {Nz, Ny, Nx} (source/demos.cpp:758-759): x is the fastest axis
-  P3M_FFT(cufftPlan3d(&s.plan_fwd, p.nz, p.ny, p.nx, dbl ? CUFFT_D2Z : CUFFT_R2C));
-  P3M_FFT(cufftPlan3d(&s.plan_inv, p.nz, p.ny, p.nx, dbl ? CUFFT_Z2D : CUFFT_C2R));
-  s.plans = true;
-  P3M_FFT(cufftSetStream(s.plan_fwd, c->stream));
-  P3M_FFT(cufftSetStream(s.plan_inv, c->stream));
   return 0;
 }
 
@@ -252,6 +302,12 @@ int poisson(p3m_ctx* c) {
   if (!c->have_density) return fail(P3M_ESTATE, "p3m_poisson: no density (call p3m_deposit)");
   State<T>& s = Sel<T>::st(c);
   const long long hc = half_count(c->prm);
+  if (c->slab) {
+    P3M_TRY(slab_poisson<T>(c));
+    P3M_TRY(slab_spread_potential<T>(c));
+    c->have_potential = true;
+    return 0;
+  }
   phase_begin(c, PH_FFT_FWD);
   P3M_FFT(exec_fwd(s.plan_fwd, s.density, s.spectrum));
   c->launches += 2;
@@ -274,12 +330,20 @@ __global__ void k_convert(const T* __restrict__ in, O* __restrict__ out, long lo
   if (i < n) out[i] = (O)in[i];
 }
 
+// Full-mesh readback.  Slab-decomposed mesh: `dev` is this rank's FFT slab; its planes are placed at their
+// position in the full array and every other plane reads 0 (sum over ranks = the full mesh).
 template <typename T, typename O>
 int get_mesh(p3m_ctx* c, const T* dev, O* out, long long count) {
   if (!dev) return fail(P3M_ESTATE, "mesh not available");
   O* stage = nullptr;
   P3M_CUDA(cudaMallocAsync((void**)&stage, sizeof(O) * (size_t)count, c->stream));
-  k_convert<T, O><<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(dev, stage, count);
+  if (c->slab) {
+    const long long share = count / c->nranks;
+    P3M_CUDA(cudaMemsetAsync(stage, 0, sizeof(O) * (size_t)count, c->stream));
+    k_convert<T, O><<<(unsigned)((share + 255) / 256), 256, 0, c->stream>>>(dev, stage + share * c->rank, share);
+  } else {
+    k_convert<T, O><<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(dev, stage, count);
+  }
   P3M_LAUNCH_CHECK(c);
   P3M_CUDA(cudaMemcpyAsync(out, stage, sizeof(O) * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
   P3M_CUDA(cudaFreeAsync(stage, c->stream));
@@ -292,7 +356,12 @@ int set_mesh(p3m_ctx* c, T* dev, const I* in, long long count) {
   I* stage = nullptr;
   P3M_CUDA(cudaMallocAsync((void**)&stage, sizeof(I) * (size_t)count, c->stream));
   P3M_CUDA(cudaMemcpyAsync(stage, in, sizeof(I) * (size_t)count, cudaMemcpyHostToDevice, c->stream));
-  k_convert<I, T><<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(stage, dev, count);
+  if (c->slab) {  // keep this rank's planes of the full array
+    const long long share = count / c->nranks;
+    k_convert<I, T><<<(unsigned)((share + 255) / 256), 256, 0, c->stream>>>(stage + share * c->rank, dev, share);
+  } else {
+    k_convert<I, T><<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(stage, dev, count);
+  }
   P3M_LAUNCH_CHECK(c);
   P3M_CUDA(cudaFreeAsync(stage, c->stream));
   P3M_CUDA(cudaStreamSynchronize(c->stream));

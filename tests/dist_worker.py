@@ -37,7 +37,10 @@ def run_case(name, p, pos, vel, mass, p3m, steps):
     ctx.force()
     info = ctx.rank_info()
     acc = allsum(ctx.get_particles(capi.UNITS_CODE, want=("acc",))[2])
-    rho = ctx.density(f64=True)
+    slab = bool(ctx.rank_info().get("slab", 0))
+    # slab-decomposed mesh: every rank returns its own planes (zeros elsewhere); replicated: rank 0 has all
+    rho = allsum(ctx.density(f64=True)) if slab else ctx.density(f64=True)
+    phi = allsum(ctx.potential(f64=True)) if slab else ctx.potential(f64=True)
     ctx.kick(0.5)
     done = ctx.step(steps)
     gp, gv, _ = ctx.get_particles(capi.UNITS_CODE)
@@ -52,6 +55,7 @@ def run_case(name, p, pos, vel, mass, p3m, steps):
         single.force()
         acc1 = single.get_particles(capi.UNITS_CODE, want=("acc",))[2]
         rho1 = single.density(f64=True)
+        phi1 = single.potential(f64=True)
         single.kick(0.5)
         single.step(steps)
         sp, sv, _ = single.get_particles(capi.UNITS_CODE)
@@ -59,7 +63,7 @@ def run_case(name, p, pos, vel, mass, p3m, steps):
         single.close()
         out = dict(case=name, n=int(p.n), world=world, n_local0=int(n_local0), ghosts=info["ghosts"],
                    total_after=int(counts[0]), steps_done=int(done),
-                   acc=rel_l2(acc, acc1), rho=rel_l2(rho, rho1), pos=rel_l2(gp, sp), vel=rel_l2(gv, sv),
+                   acc=rel_l2(acc, acc1), rho=rel_l2(rho, rho1), phi=rel_l2(phi, phi1), slab=int(slab), pos=rel_l2(gp, sp), vel=rel_l2(gv, sv),
                    diag=float(np.abs(diag - diag1).max() / (np.abs(diag1).max() + 1e-300)))
     return out
 

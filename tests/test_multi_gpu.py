@@ -20,18 +20,24 @@ def gpu_count():
         return 0
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_slab_decomposition_matches_single_gpu(world):
+@pytest.mark.parametrize("world,mesh", [(2, "slab"), (4, "slab"), (2, "replicated")])
+def test_slab_decomposition_matches_single_gpu(world, mesh):
+    """mesh = slab: slab-decomposed density / potential and distributed FFT (all-to-all transpose);
+    mesh = replicated: the full-mesh all-reduce fallback used when nz or ny do not divide by the ranks."""
     if gpu_count() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + world), os.path.join(HERE, "dist_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    env = dict(os.environ)
+    if mesh == "replicated":
+        env["P3M_REPLICATED_MESH"] = "1"
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("DIST_RESULTS ")][-1]
     for res in json.loads(line[len("DIST_RESULTS "):]):
+        assert res["slab"] == (mesh == "slab"), res
         assert res["total_after"] == res["n"], res          # no particle lost or duplicated
-        assert res["rho"] < 1e-5 and res["acc"] < 2e-5, res  # same force field as one GPU
+        assert res["rho"] < 1e-5 and res["phi"] < 1e-5 and res["acc"] < 2e-5, res  # same fields as one GPU
         assert res["pos"] < 1e-5 and res["vel"] < 1e-3, res  # same trajectories after the steps
         assert res["diag"] < 1e-4, res
         assert res["n_local0"] < res["n"], res               # the set really was split
