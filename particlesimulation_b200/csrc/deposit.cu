@@ -102,8 +102,10 @@ k_deposit(const V4<T>* __restrict__ posm, long long n, int chunk, const int* __r
       Stencil<T, K> s;
       int li = -1 - lane;
       bool fits = false;
+      T px = 0, py = 0, pz = 0, pm = 0;
       if (valid) {
         const V4<T> p = posm[i];
+        px = p.x, py = p.y, pz = p.z, pm = p.w;
         s = make_stencil<T, K>(p.x, p.y, p.z, p.w);
         const int rx = s.x0 - lo[0], ry = s.y0 - lo[1], rz = s.z0 - lo[2];
         fits = rx >= 0 && ry >= 0 && rz >= 0 && rx + K <= ext[0] && ry + K <= ext[1] &&
@@ -142,11 +144,17 @@ k_deposit(const V4<T>* __restrict__ posm, long long n, int chunk, const int* __r
         }
         __syncwarp();
       } else {
-        const unsigned grp = __match_any_sync(0xffffffffu, li);
-        const int rank = __popc(grp & ((1u << lane) - 1u));
-        const int maxrank = __reduce_max_sync(0xffffffffu, fits ? rank : 0);
-        for (int r = 0; r <= maxrank; ++r) {
-          const bool act = fits && rank == r;
+        // Lanes sharing a base cell: the lowest lane of each group (the leader) pulls the other members'
+        // particles through shuffles and sums all their stencils in registers, so that ONE round of
+        // read-modify-writes serves the whole batch -- leaders hold distinct base cells, hence distinct
+        // addresses for any given stencil point.
+        const unsigned grp = __match_any_sync(0xffffffffu, li) & fmask;
+        const bool leader = fits && (__ffs(grp) - 1) == lane;
+        const int members = fits ? __popc(grp) : 0;
+        const int maxmembers = __reduce_max_sync(0xffffffffu, members);
+        T v[K * K * K];
+        {
+          int q = 0;
 #pragma unroll
           for (int a = 0; a < K; ++a) {
             const T t1 = s.pref * s.wx[a];
@@ -154,12 +162,43 @@ k_deposit(const V4<T>* __restrict__ posm, long long n, int chunk, const int* __r
             for (int b = 0; b < K; ++b) {
               const T t2 = t1 * s.wy[b];
 #pragma unroll
-              for (int cc = 0; cc < K; ++cc) {
-                if (act) tile[li + (cc * ext[1] + b) * ext[0] + a] += t2 * s.wz[cc];
-                __syncwarp();  // orders the RMW of different lanes on overlapping stencils
+              for (int cc = 0; cc < K; ++cc, ++q) v[q] = t2 * s.wz[cc];
+            }
+          }
+        }
+        unsigned rest = leader ? (grp & ~(1u << lane)) : 0u;
+        for (int r = 1; r < maxmembers; ++r) {
+          const bool pull = rest != 0u;
+          const int src = pull ? __ffs(rest) - 1 : lane;
+          rest &= rest - 1u;
+          const T qx = __shfl_sync(0xffffffffu, px, src), qy = __shfl_sync(0xffffffffu, py, src),
+                  qz = __shfl_sync(0xffffffffu, pz, src), qm = __shfl_sync(0xffffffffu, pm, src);
+          if (pull) {
+            const Stencil<T, K> o = make_stencil<T, K>(qx, qy, qz, qm);
+            int q = 0;
+#pragma unroll
+            for (int a = 0; a < K; ++a) {
+              const T t1 = o.pref * o.wx[a];
+#pragma unroll
+              for (int b = 0; b < K; ++b) {
+                const T t2 = t1 * o.wy[b];
+#pragma unroll
+                for (int cc = 0; cc < K; ++cc, ++q) v[q] += t2 * o.wz[cc];
               }
             }
           }
+        }
+        {
+          int q = 0;
+#pragma unroll
+          for (int a = 0; a < K; ++a)
+#pragma unroll
+            for (int b = 0; b < K; ++b)
+#pragma unroll
+              for (int cc = 0; cc < K; ++cc, ++q) {
+                if (leader) tile[li + (cc * ext[1] + b) * ext[0] + a] += v[q];
+                __syncwarp();  // orders the RMW of different lanes on overlapping stencils
+              }
         }
       }
     }

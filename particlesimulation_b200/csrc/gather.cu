@@ -12,6 +12,8 @@
 // (only the potential wraps periodically, source/grid.cpp:46-48,66-68).  Particles whose stencil leaves
 // [0,N) on some axis -- where the unwrapped index aliases into a neighbouring row -- take the exact
 // per-cell path below instead of the tile.
+#include <algorithm>
+
 #include "ctx.cuh"
 #include "stencil.cuh"
 
@@ -191,6 +193,122 @@ k_gather(const V4<T>* __restrict__ posm, long long n, int chunk, const int* __re
   }
 }
 
+// ---- PM-only contexts: compile-time tile, potential tile only -------------------------------------------
+// The binning cells are 8^3 mesh cells and particles are sorted by (Morton(binning cell), mesh cell,
+// id), so 4 consecutive binning cells = one 16 x 16 x 8 block of mesh cells = one contiguous run of
+// particles.  A CTA stages the POTENTIAL of that block (+ assignment and finite-difference halo, periodic
+// wrap applied while staging) and every particle differences and interpolates straight from it: no E
+// tile, one barrier per block, every shared-memory offset a compile-time immediate.  The arithmetic per
+// stencil point is the reference's (E = -1/2 (phi[+1] - phi[-1]), then sum w E); the power-of-two
+// factors -1/2 and 1/8 are applied once at the end, which is exact in binary floating point.
+template <int FD>
+struct PmTile {
+  static constexpr int TX = 16, TY = 16, TZ = 8;
+  static constexpr int HALO = 1 + FD;  // assignment stencil reach + finite-difference reach
+  static constexpr int PX = TX + 2 * HALO, PY = TY + 2 * HALO, PZ = TZ + 2 * HALO;
+  static constexpr int ELEMS = PX * PY * PZ;
+};
+constexpr int kGatherPmDirect = 48;  // blocks with fewer particles read the potential straight from L2
+
+template <typename T, int K, int FD>
+__global__ void __launch_bounds__(256, 3)
+k_gather_pm(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start, Geom<T> g,
+            const T* __restrict__ phi, V4<T>* __restrict__ acc) {
+  using TL = PmTile<FD>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sphi = reinterpret_cast<T*>(smem_raw);
+  const int tid = threadIdx.x;
+  const long long ncells = 1LL << (3 * g.mbits);
+  const long long c0 = 4LL * blockIdx.x;
+  const int s = cell_start[c0], e = cell_start[c0 + 4 < ncells ? c0 + 4 : ncells];
+  const int count = e - s;
+  if (count <= 0) return;
+  // large blocks (clustered sets) are split over blockIdx.y
+  int per = (count + (int)gridDim.y - 1) / (int)gridDim.y;
+  per = max(2048, (per + 255) & ~255);
+  const int my0 = s + (int)blockIdx.y * per, my1 = min(e, my0 + per);
+  if (my0 >= my1) return;
+  const T scale = (K == 3) ? T(0.125) : T(1);
+  if (count < kGatherPmDirect) {
+    for (int i = my0 + tid; i < my1; i += 256) {
+      const V4<T> p = posm[i];
+      const Stencil<T, K> st = make_stencil<T, K>(p.x, p.y, p.z, p.w);
+      T ax = 0, ay = 0, az = 0;
+      gather_direct<T, K, FD>(st, g, phi, ax, ay, az);
+      add_external(g, p.x, p.y, p.z, ax, ay, az);
+      acc[i] = V4<T>{ax, ay, az, 0};
+    }
+    return;
+  }
+  // first staged mesh index on each axis
+  const int ox = ((int)compact3((uint32_t)c0) << kPmTileShift) - TL::HALO;
+  const int oy = ((int)compact3((uint32_t)c0 >> 1) << kPmTileShift) - TL::HALO;
+  const int oz = ((int)compact3((uint32_t)c0 >> 2) << kPmTileShift) - TL::HALO;
+  for (int el = tid; el < TL::ELEMS; el += 256) {
+    const int iz = el / (TL::PX * TL::PY), r = el - iz * (TL::PX * TL::PY);
+    const int iy = r / TL::PX, ix = r - iy * TL::PX;
+    const int gx = wrap_idx(ox + ix, g.nx), gy = wrap_idx(oy + iy, g.ny), gz = pot_plane(g, oz + iz);
+    sphi[el] = gz < 0 ? T(0) : phi[(long long)gx + (long long)gy * g.nx + (long long)gz * g.nx * g.ny];
+  }
+  __syncthreads();
+  constexpr int SY = TL::PX, SZ = TL::PX * TL::PY;
+  for (int i = my0 + tid; i < my1; i += 256) {
+    const V4<T> p = posm[i];
+    const Stencil<T, K> st = make_stencil<T, K>(p.x, p.y, p.z, p.w);
+    const int rx = st.x0 - ox, ry = st.y0 - oy, rz = st.z0 - oz;
+    const bool fits = rx >= FD && ry >= FD && rz >= FD && rx + K + FD <= TL::PX && ry + K + FD <= TL::PY &&
+                      rz + K + FD <= TL::PZ && st.x0 >= 0 && st.y0 >= 0 && st.z0 >= 0 &&
+                      st.x0 + K <= g.nx && st.y0 + K <= g.ny && st.z0 + K <= g.nz;
+    T ax = 0, ay = 0, az = 0;
+    if (fits) {
+      const T* base = sphi + (rz * TL::PY + ry) * TL::PX + rx;
+#pragma unroll
+      for (int a = 0; a < K; ++a)
+#pragma unroll
+        for (int b = 0; b < K; ++b)
+#pragma unroll
+          for (int cc = 0; cc < K; ++cc) {
+            const T* q = base + (cc * TL::PY + b) * TL::PX + a;
+            if (FD == 1) {
+              const T w = (st.wx[a] * st.wy[b]) * st.wz[cc];
+              ax += w * (q[1] - q[-1]), ay += w * (q[SY] - q[-SY]), az += w * (q[SZ] - q[-SZ]);
+            } else {
+              const T w = scale * ((st.wx[a] * st.wy[b]) * st.wz[cc]);
+              const T k = T(-1.0) / 12;
+              ax += w * (k * (-q[2] + 8 * q[1] - 8 * q[-1] + q[-2]));
+              ay += w * (k * (-q[2 * SY] + 8 * q[SY] - 8 * q[-SY] + q[-2 * SY]));
+              az += w * (k * (-q[2 * SZ] + 8 * q[SZ] - 8 * q[-SZ] + q[-2 * SZ]));
+            }
+          }
+      if (FD == 1) {
+        const T f = T(-0.5) * scale;
+        ax *= f, ay *= f, az *= f;
+      }
+    } else {
+      gather_direct<T, K, FD>(st, g, phi, ax, ay, az);
+    }
+    add_external(g, p.x, p.y, p.z, ax, ay, az);
+    acc[i] = V4<T>{ax, ay, az, 0};
+  }
+}
+
+template <typename T, int K, int FD>
+static int launch_gather_pm(p3m_ctx* c) {
+  State<T>& s = Sel<T>::st(c);
+  const Geom<T>& g = Sel<T>::g(c);
+  const long long ncells = 1LL << (3 * g.mbits);
+  const unsigned blocks = (unsigned)((ncells + 3) / 4);
+  // one CTA per block; a block holding very many particles (a clustered set in a PM-only run) is walked
+  // by its CTA in passes of 256.  gridDim.y is the hook for splitting such blocks.
+  const int split = 1;
+  auto kern = k_gather_pm<T, K, FD>;
+  const size_t smem = sizeof(T) * PmTile<FD>::ELEMS;
+  P3M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<dim3(blocks, split), 256, smem, c->stream>>>(s.posm, s.cell_start, g, s.pot_part, s.acc);
+  P3M_LAUNCH_CHECK(c);
+  return 0;
+}
+
 template <typename T, int K, int FD>
 static int launch_gather(p3m_ctx* c) {
   State<T>& s = Sel<T>::st(c);
@@ -218,7 +336,17 @@ int gather(p3m_ctx* c) {
   const Geom<T>& g = Sel<T>::g(c);
   phase_begin(c, PH_GATHER);
   int r = 0;
-  if (c->n > 0) {
+  const bool pm_tiles = !g.p3m && g.tile_shift == kPmTileShift && g.sbits == g.tile_shift;
+  if (c->n > 0 && pm_tiles) {
+    const int k = g.is == P3M_TSC ? 3 : (g.is == P3M_CIC ? 2 : 1);
+    const int fd = g.fds == P3M_TWO_POINT ? 1 : 2;
+    if (k == 3 && fd == 1) r = launch_gather_pm<T, 3, 1>(c);
+    else if (k == 3 && fd == 2) r = launch_gather_pm<T, 3, 2>(c);
+    else if (k == 2 && fd == 1) r = launch_gather_pm<T, 2, 1>(c);
+    else if (k == 2 && fd == 2) r = launch_gather_pm<T, 2, 2>(c);
+    else if (k == 1 && fd == 1) r = launch_gather_pm<T, 1, 1>(c);
+    else r = launch_gather_pm<T, 1, 2>(c);
+  } else if (c->n > 0) {
     const int k = g.is == P3M_TSC ? 3 : (g.is == P3M_CIC ? 2 : 1);
     const int fd = g.fds == P3M_TWO_POINT ? 1 : 2;
     if (k == 3 && fd == 1) r = launch_gather<T, 3, 1>(c);

@@ -1,0 +1,7 @@
+# multi-GPU measurements (run under gpurun --gpus N): C2 weak scaling + C3 mesh config, N from $1
+set -u
+N=${1:-2}
+mkdir -p gpurun_out
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
+timeout 600 $TR bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/bench_g${N}_c2.log 2>&1; tail -1 gpurun_out/bench_g${N}_c2.log | cut -c1-1500
+timeout 600 $TR bench.py --gpus $N --config mesh --steps 3 --warmup 2 > gpurun_out/bench_g${N}_mesh.log 2>&1; tail -1 gpurun_out/bench_g${N}_mesh.log | cut -c1-1500
