@@ -297,6 +297,7 @@ def run_mesh_config(args):
                 "poisson": hbm(18.0 * M, ph["forwardFFT"] + ph["fourierPotential"] + ph["inverseFFT"]),
                 "updateAccelerations": hbm(4.0 * M + 28.0 * n, ph["updateAccelerations"]),
                 "integrate": hbm(96.0 * n, ph["integrate"])},
+            "ms_per_step_by_phase": {k: round(v, 4) for k, v in ph.items()},
             "hbm_peak": hbm_peak, "hbm_peak_source": peak_src}
     print(json.dumps(line))
 

@@ -298,16 +298,28 @@ int bin_sort(p3m_ctx* c) {
   } else if (3 * g.mbits + 3 * g.tile_shift + idbits <= 62) {
     g.sbits = g.tile_shift;  // PM: sub key = mesh cell inside the tile (sort_kernels.cuh)
   }
-  const int keybits = idbits + 3 * g.sbits + 3 * g.mbits;
+  // PM-only contexts sort on a 32-bit (tile, mesh cell) key without the id (see k_keys)
+  const bool short_key = !g.p3m && 3 * g.mbits + 3 * g.sbits <= 32 && !getenv("P3M_TUNE_LONGKEY");
+  const int lowbits = (short_key ? 0 : idbits) + 3 * g.sbits;
+  const int keybits = lowbits + 3 * g.mbits;
   const long long ncells = 1LL << (3 * g.mbits);
+  uint32_t* keys32 = reinterpret_cast<uint32_t*>(s.keys);
+  uint32_t* keys32_alt = reinterpret_cast<uint32_t*>(s.keys_alt);
   phase_begin(c, PH_BINSORT);
   if (n > 0) {
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    k_keys<T><<<blocks, 256, 0, c->stream>>>(s.posm, s.id, n, g, s.keys, s.slots, s.flags);
-    P3M_LAUNCH_CHECK(c);
     size_t tmp = s.cub_tmp_bytes;
-    P3M_CUDA(cub::DeviceRadixSort::SortPairs(s.cub_tmp, tmp, s.keys, s.keys_alt, s.slots, s.slots_alt,
-                                             (int)n, 0, keybits, c->stream));
+    if (short_key) {
+      k_keys<T, uint32_t><<<blocks, 256, 0, c->stream>>>(s.posm, s.id, n, g, keys32, s.slots, s.flags);
+      P3M_LAUNCH_CHECK(c);
+      P3M_CUDA(cub::DeviceRadixSort::SortPairs(s.cub_tmp, tmp, keys32, keys32_alt, s.slots, s.slots_alt, (int)n, 0,
+                                               keybits, c->stream));
+    } else {
+      k_keys<T, uint64_t><<<blocks, 256, 0, c->stream>>>(s.posm, s.id, n, g, s.keys, s.slots, s.flags);
+      P3M_LAUNCH_CHECK(c);
+      P3M_CUDA(cub::DeviceRadixSort::SortPairs(s.cub_tmp, tmp, s.keys, s.keys_alt, s.slots, s.slots_alt,
+                                               (int)n, 0, keybits, c->stream));
+    }
     c->launches += (keybits + 7) / 8 + 1;
     k_permute<T><<<blocks, 256, 0, c->stream>>>(s.slots_alt, n, s.posm, s.vel, s.id, s.posm_alt,
                                                 s.vel_alt, s.id_alt);
@@ -321,8 +333,12 @@ int bin_sort(p3m_ctx* c) {
       P3M_LAUNCH_CHECK(c);
     }
   }
-  k_cell_start<<<(unsigned)((ncells + 1 + 255) / 256), 256, 0, c->stream>>>(s.keys_alt, n, idbits + 3 * g.sbits,
-                                                                           ncells, s.cell_start);
+  if (short_key)
+    k_cell_start<uint32_t><<<(unsigned)((ncells + 1 + 255) / 256), 256, 0, c->stream>>>(keys32_alt, n, lowbits, ncells,
+                                                                                       s.cell_start);
+  else
+    k_cell_start<uint64_t><<<(unsigned)((ncells + 1 + 255) / 256), 256, 0, c->stream>>>(s.keys_alt, n, lowbits, ncells,
+                                                                                       s.cell_start);
   P3M_LAUNCH_CHECK(c);
   phase_end(c, PH_BINSORT);
   c->sorted = true;
@@ -423,6 +439,7 @@ void free_state(p3m_ctx* c) {
                   s.pp_counters, s.pair_counts, s.flags, s.diag};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  if (s.twiddle_z) cudaFree(s.twiddle_z);
   if (s.plans) {
     cufftDestroy(s.plan_fwd);
     cufftDestroy(s.plan_inv);

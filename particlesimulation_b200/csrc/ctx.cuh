@@ -61,6 +61,9 @@ struct State {
   double* diag = nullptr;  // 16 doubles
   cufftHandle plan_fwd = 0, plan_inv = 0;
   bool plans = false;
+  // fused z pass (poisson_z.cu): plan_fwd / plan_inv are then batched 2-D transforms over `fft_chunk` planes
+  void* twiddle_z = nullptr;  // W_nz^k, k < nz
+  int fft_chunk = 0;
 };
 
 }  // namespace p3m
@@ -99,6 +102,7 @@ struct p3m_ctx {
   void* nccl_comm = nullptr;  // ncclComm_t
   int rank = 0, nranks = 1;
   long long n_global = 0;
+  bool fused_z = false;       // z leg of the Poisson solve = k_poisson_z (power-of-two nz), else cuFFT
   bool slab = false;          // slab-decomposed mesh + distributed FFT (else: replicated mesh, all-reduce)
   // static plane ranges of every rank (identical on all ranks): density planes deposited by the
   // particle slab, unwrapped potential planes its gather needs
@@ -173,6 +177,11 @@ void dist_destroy(p3m_ctx* c);
 template <typename T> int dist_migrate(p3m_ctx* c, bool exchange);
 template <typename T> int dist_ghosts(p3m_ctx* c);
 template <typename T> int dist_allreduce_density(p3m_ctx* c);
+// poisson_z.cu: forward z FFT + influence-function multiply + inverse z FFT in one pass
+bool fused_z_supported(int nz);
+template <typename T> int fused_z_init(p3m_ctx* c);
+template <typename T> int fused_z_pass(p3m_ctx* c, void* spec, const T* green, long long ncols);
+int fft_chunk_planes(long long plane_bytes, int planes);
 // dist_mesh.cu: slab-decomposed mesh
 template <typename T> int slab_setup(p3m_ctx* c);             // after dist_init: plane ranges, buffers, plans
 template <typename T> void slab_free(p3m_ctx* c);

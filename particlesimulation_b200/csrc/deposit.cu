@@ -16,6 +16,9 @@
 //     skipping zeros;
 //   * runs too short to amortise a tile (sparse outskirts) go straight to global REDG.
 // Algorithmic HBM traffic: 16 B/particle read + 4 B/cell written (+ 4 B/cell memset).
+#include <cstdlib>
+
+#include "async_copy.cuh"
 #include "ctx.cuh"
 #include "stencil.cuh"
 
@@ -226,6 +229,187 @@ k_deposit(const V4<T>* __restrict__ posm, long long n, int chunk, const int* __r
   }
 }
 
+// ---- PM-only contexts: one thread per mesh cell ----------------------------------------------------------
+// Binning cells are 8^3 mesh cells and the sort key orders the particles of a binning cell by mesh cell
+// (x fastest), so each mesh cell is a contiguous run.  A CTA of 512 threads takes one binning cell:
+//   1. stage its particles in shared memory and find every mesh cell's run from the head / tail positions
+//      (cell id differs from the neighbour's) -- no atomics, no scan;
+//   2. thread t sums the K^3 stencil contributions of all particles of mesh cell t IN REGISTERS;
+//   3. K^3 read-modify-write rounds on a 10^3 shared tile: in one round every thread adds the same stencil
+//      offset, so all addresses are distinct (no atomics needed -- sm_100a has no native shared float add);
+//      rounds along x only interact inside a warp (__syncwarp), a change of the (y, z) offset is a
+//      __syncthreads.  Row pitch 24 keeps the 4 rows of a warp in disjoint banks;
+//   4. the tile goes to the global mesh with native REDG.ADD, zeros skipped.
+// Duplicates, rank rounds and match.any of the generic kernel disappear; the work per particle is the
+// register FMAs only.  Non-empty binning cells come from a compacted list (k_occupied_cells), walked by a
+// persistent grid.
+__global__ void k_occupied_cells(const int* __restrict__ cell_start, long long ncells, int* __restrict__ list,
+                                 int* __restrict__ counter) {
+  const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  if (cell_start[c + 1] > cell_start[c]) list[atomicAdd(counter, 1)] = (int)c;
+}
+
+template <typename T, int K>
+__global__ void __launch_bounds__(512, 2)
+k_deposit_pm(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start, const int* __restrict__ list,
+             const int* __restrict__ counter, Geom<T> g, T* __restrict__ density) {
+  constexpr int TE = 10, TP = 24, CAP = sizeof(T) == 8 ? 256 : 1024, B = 1 << kPmTileShift;
+  constexpr int O = (K == 3) ? 0 : 1;  // tile coordinate of stencil point 0 of local cell 0 (tile origin = cell - 1)
+  __shared__ __align__(16) V4<T> sp_all[2][CAP];  // double buffer: item k+1 lands while item k is processed
+  __shared__ T tile[TE * TE * TP];
+  __shared__ short cid[CAP + 2];
+  __shared__ short first[B * B * B], last[B * B * B];
+  __shared__ uint64_t bar[2];
+  __shared__ int meta[2][3];  // (cell, s, e) of the item whose first CAP particles are in buffer b
+  const int tid = threadIdx.x;
+  const int lx = tid & (B - 1), ly = (tid >> kPmTileShift) & (B - 1), lz = tid >> (2 * kPmTileShift);
+  const int nocc = *counter;
+  const int G = gridDim.x;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1), mbar_init(&bar[1], 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  // thread 0 runs the copy pipeline: `cell_next` is the binning cell of the NEXT item
+  int cell_next = -1;
+  if (tid == 0 && (int)blockIdx.x < nocc) {
+    const int c0 = list[blockIdx.x];
+    const int s0 = cell_start[c0], e0 = cell_start[c0 + 1];
+    meta[0][0] = c0, meta[0][1] = s0, meta[0][2] = e0;
+    const uint32_t bytes = (uint32_t)min(CAP, e0 - s0) * (uint32_t)sizeof(V4<T>);
+    mbar_arrive_expect_tx(&bar[0], bytes);
+    bulk_copy_g2s(sp_all[0], posm + s0, bytes, &bar[0]);
+    if ((int)blockIdx.x + G < nocc) cell_next = list[blockIdx.x + G];
+  }
+  __syncthreads();
+  int it = 0;
+  for (int w = blockIdx.x; w < nocc; w += G, ++it) {
+    const int bsel = it & 1;
+    V4<T>* sp = sp_all[bsel];
+    // metadata of the next item: loads issued now, consumed after the first barrier below
+    int s_n = 0, e_n = 0, cell_nn = -1;
+    if (tid == 0 && cell_next >= 0) {
+      s_n = cell_start[cell_next], e_n = cell_start[cell_next + 1];
+      if (w + 2 * G < nocc) cell_nn = list[w + 2 * G];
+    }
+    const uint32_t cell = (uint32_t)meta[bsel][0];
+    const int s = meta[bsel][1], e = meta[bsel][2];
+    const int ox = (int)compact3(cell) << kPmTileShift, oy = (int)compact3(cell >> 1) << kPmTileShift,
+              oz = (int)compact3(cell >> 2) << kPmTileShift;
+    for (int el = tid; el < TE * TE * TP; el += 512) tile[el] = T(0);
+    T* mytile = tile + ((lz + O) * TE + (ly + O)) * TP + lx + O;
+    mbar_wait(&bar[bsel], (uint32_t)((it >> 1) & 1));  // this item's particles have landed
+    for (int pass = s; pass < e; pass += CAP) {
+      const int n = min(CAP, e - pass);
+      first[tid] = 0, last[tid] = 0;
+      if (tid == 0) cid[0] = -2, cid[n + 1] = -3;
+      bool stray = false;
+      for (int k = tid; k < n; k += 512) {
+        V4<T> p;
+        if (pass == s) {
+          p = sp[k];
+        } else {  // runs longer than CAP: later passes are loaded synchronously
+          p = posm[pass + k];
+          sp[k] = p;
+        }
+        const int bx = (int)p.x - ox, by = (int)p.y - oy, bz = (int)p.z - oz;  // base cell
+        const bool in = bx >= 0 && by >= 0 && bz >= 0 && bx < B && by < B && bz < B;
+        cid[k + 1] = in ? (short)((bz * B + by) * B + bx) : (short)-1;
+        stray |= !in;
+      }
+      const bool any_stray = __syncthreads_or(stray);
+      if (pass == s && tid == 0 && cell_next >= 0) {
+        // the other buffer was released by the barrier at the end of the previous item: start the next copy
+        meta[bsel ^ 1][0] = cell_next, meta[bsel ^ 1][1] = s_n, meta[bsel ^ 1][2] = e_n;
+        const uint32_t bytes = (uint32_t)min(CAP, e_n - s_n) * (uint32_t)sizeof(V4<T>);
+        proxy_fence_async();
+        mbar_arrive_expect_tx(&bar[bsel ^ 1], bytes);
+        bulk_copy_g2s(sp_all[bsel ^ 1], posm + s_n, bytes, &bar[bsel ^ 1]);
+      }
+      if (any_stray) {
+        // a particle binned here by clamping (outside the mesh): exact global path for this pass
+        for (int k = tid; k < n; k += 512) {
+          const V4<T> p = sp[k];
+          const Stencil<T, K> st = make_stencil<T, K>(p.x, p.y, p.z, p.w);
+          deposit_direct<T, K>(st, g, density);
+        }
+        __syncthreads();
+        continue;
+      }
+      for (int k = tid; k < n; k += 512) {
+        const int c0 = cid[k + 1];
+        if (c0 != cid[k]) first[c0] = (short)k;
+        if (c0 != cid[k + 2]) last[c0] = (short)(k + 1);
+      }
+      __syncthreads();
+      // registers: the K^3 stencil sums of this thread's mesh cell (runs longer than CAP simply take several
+      // passes, each followed by its own read-modify-write rounds)
+      T acc[K * K * K];
+#pragma unroll
+      for (int q = 0; q < K * K * K; ++q) acc[q] = T(0);
+      const int j0 = first[tid], j1 = last[tid];
+      for (int j = j0; j < j1; ++j) {
+        const V4<T> p = sp[j];
+        const Stencil<T, K> st = make_stencil<T, K>(p.x, p.y, p.z, p.w);
+#pragma unroll
+        for (int a = 0; a < K; ++a) {
+          const T t1 = st.pref * st.wx[a];
+#pragma unroll
+          for (int b = 0; b < K; ++b) {
+            const T t2 = t1 * st.wy[b];
+#pragma unroll
+            for (int cc = 0; cc < K; ++cc) acc[(a * K + b) * K + cc] += t2 * st.wz[cc];
+          }
+        }
+      }
+      const bool mine = j1 > j0;
+#pragma unroll
+      for (int cc = 0; cc < K; ++cc)
+#pragma unroll
+        for (int b = 0; b < K; ++b) {
+          __syncthreads();  // rows of other warps (the first one also fences sp / cid / first / last)
+#pragma unroll
+          for (int a = 0; a < K; ++a) {
+            if (mine) mytile[(cc * TE + b) * TP + a] += acc[(a * K + b) * K + cc];
+            __syncwarp();  // x neighbours live in the same warp
+          }
+        }
+    }
+    cell_next = cell_nn;
+    __syncthreads();
+    for (int el = tid; el < TE * TE * TE; el += 512) {
+      const int iz = el / (TE * TE), r = el - iz * (TE * TE), iy = r / TE, ix = r - iy * TE;
+      const T v = tile[(iz * TE + iy) * TP + ix];
+      if (v != T(0)) {
+        // Grid::getIndx, unwrapped (include/grid.h:52-54)
+        long long flat = (long long)(ox - 1 + ix) + (long long)(oy - 1 + iy) * g.nx +
+                         (long long)(oz - 1 + iz) * g.nx * g.ny;
+        if (flat >= 0 && flat < g.M) {
+          flat -= g.den_off;
+          if (flat >= 0 && flat < g.den_len) atomicAdd(&density[flat], v);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T, int K>
+static int launch_deposit_pm(p3m_ctx* c) {
+  State<T>& s = Sel<T>::st(c);
+  const Geom<T>& g = Sel<T>::g(c);
+  const long long ncells = 1LL << (3 * g.mbits);
+  int* list = s.pp_items;  // free in PM-only contexts; sized >= ncells entries
+  int* counter = s.pp_counters + 6;
+  P3M_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), c->stream));
+  k_occupied_cells<<<(unsigned)((ncells + 255) / 256), 256, 0, c->stream>>>(s.cell_start, ncells, list, counter);
+  P3M_LAUNCH_CHECK(c);
+  k_deposit_pm<T, K><<<c->num_sms * 2, 512, 0, c->stream>>>(s.posm, s.cell_start, list, counter, g, s.dens_part);
+  P3M_LAUNCH_CHECK(c);
+  return 0;
+}
+
 template <typename T, int K>
 static int launch_deposit(p3m_ctx* c) {
   State<T>& s = Sel<T>::st(c);
@@ -258,7 +442,11 @@ int deposit(p3m_ctx* c) {
   P3M_CUDA(cudaMemsetAsync(s.dens_part, 0, sizeof(T) * (size_t)g.den_len, c->stream));
   c->launches++;
   int r = 0;
-  if (c->n > 0) {
+  const bool pm_cells = !g.p3m && g.tile_shift == kPmTileShift && g.sbits == g.tile_shift && g.is != P3M_NGP &&
+                        !getenv("P3M_TUNE_OLD_DEPOSIT");
+  if (c->n > 0 && pm_cells) {
+    r = g.is == P3M_TSC ? launch_deposit_pm<T, 3>(c) : launch_deposit_pm<T, 2>(c);
+  } else if (c->n > 0) {
     if (g.is == P3M_TSC)
       r = launch_deposit<T, 3>(c);
     else if (g.is == P3M_CIC)

@@ -354,7 +354,7 @@ int dist_ghosts(p3m_ctx* c) {
   // sort the ghosts by the same (cell, sub-cell, id) key and index them by cell
   if (ng > 0) {
     const unsigned blocks = (unsigned)((ng + 255) / 256);
-    k_keys<T><<<blocks, 256, 0, c->stream>>>(s.gposm, s.gid, ng, g, s.keys, s.slots, s.flags);
+    k_keys<T, uint64_t><<<blocks, 256, 0, c->stream>>>(s.gposm, s.gid, ng, g, s.keys, s.slots, s.flags);
     P3M_LAUNCH_CHECK(c);
     size_t tmp = s.cub_tmp_bytes;
     const int keybits = g.idbits + 3 * g.sbits + 3 * g.mbits;
@@ -369,7 +369,7 @@ int dist_ghosts(p3m_ctx* c) {
     k_tile_aabb<T><<<(unsigned)((tiles * 32 + 255) / 256), 256, 0, c->stream>>>(s.gposm, ng, s.gaabb);
     P3M_LAUNCH_CHECK(c);
   }
-  k_cell_start<<<(unsigned)((ncells + 1 + 255) / 256), 256, 0, c->stream>>>(s.keys_alt, ng, g.idbits + 3 * g.sbits,
+  k_cell_start<uint64_t><<<(unsigned)((ncells + 1 + 255) / 256), 256, 0, c->stream>>>(s.keys_alt, ng, g.idbits + 3 * g.sbits,
                                                                            ncells, s.gcell_start);
   P3M_LAUNCH_CHECK(c);
   phase_end(c, PH_COMM);

@@ -161,17 +161,20 @@ int slab_setup(p3m_ctx* c) {
   P3M_CUDA(cudaMemsetAsync(s.pot_part, 0, sizeof(T) * plane * (size_t)c->pot_nz[me], c->stream));
   const bool dbl = sizeof(T) == 8;
   int n2[2] = {g.ny, g.nx};
-  P3M_FFT(cufftPlanMany(&s.plan_fwd, 2, n2, nullptr, 1, 0, nullptr, 1, 0, dbl ? CUFFT_D2Z : CUFFT_R2C, nzl));
-  P3M_FFT(cufftPlanMany(&s.plan_inv, 2, n2, nullptr, 1, 0, nullptr, 1, 0, dbl ? CUFFT_Z2D : CUFFT_C2R, nzl));
+  s.fft_chunk = fft_chunk_planes((long long)nxh * g.ny * sizeof(cplx), nzl);
+  P3M_FFT(cufftPlanMany(&s.plan_fwd, 2, n2, nullptr, 1, 0, nullptr, 1, 0, dbl ? CUFFT_D2Z : CUFFT_R2C, s.fft_chunk));
+  P3M_FFT(cufftPlanMany(&s.plan_inv, 2, n2, nullptr, 1, 0, nullptr, 1, 0, dbl ? CUFFT_Z2D : CUFFT_C2R, s.fft_chunk));
   s.plans = true;
-  int n1[1] = {g.nz};
-  int embed[1] = {g.nz};
-  const int stride = nxh * nyl;
-  P3M_FFT(cufftPlanMany(&s.plan_z, 1, n1, embed, stride, 1, embed, stride, 1, dbl ? CUFFT_Z2Z : CUFFT_C2C, stride));
-  s.plan_z_made = true;
   P3M_FFT(cufftSetStream(s.plan_fwd, c->stream));
   P3M_FFT(cufftSetStream(s.plan_inv, c->stream));
-  P3M_FFT(cufftSetStream(s.plan_z, c->stream));
+  if (!c->fused_z) {  // z leg through cuFFT (nz not a power of two): strided batched 1-D transforms
+    int n1[1] = {g.nz};
+    int embed[1] = {g.nz};
+    const int stride = nxh * nyl;
+    P3M_FFT(cufftPlanMany(&s.plan_z, 1, n1, embed, stride, 1, embed, stride, 1, dbl ? CUFFT_Z2Z : CUFFT_C2C, stride));
+    s.plan_z_made = true;
+    P3M_FFT(cufftSetStream(s.plan_z, c->stream));
+  }
   return 0;
 }
 
@@ -288,35 +291,47 @@ int slab_poisson(p3m_ctx* c) {
   const long long spec = (long long)nxh * g.ny * nzl;
   const size_t chunk = (size_t)nxh * nyl * nzl;
   const int grid = grid_for(spec, c->num_sms);
+  const size_t plane = (size_t)g.nx * g.ny, splane = (size_t)nxh * g.ny;
   phase_begin(c, PH_FFT_FWD);
-  P3M_FFT(exec_r2c(s.plan_fwd, s.density, s.spectrum));
+  for (int z = 0; z < nzl; z += s.fft_chunk) {
+    P3M_FFT(exec_r2c(s.plan_fwd, s.density + plane * z, s.spectrum + splane * z));
+    c->launches += 2;
+  }
   k_transpose_pack<cplx, true><<<grid, 256, 0, c->stream>>>(s.spectrum, s.pack, nxh, g.ny, nyl, nzl);
   P3M_LAUNCH_CHECK(c);
-  c->launches += 2;
+  c->launches += 1;
   phase_end(c, PH_FFT_FWD);
   phase_begin(c, PH_COMM);
   P3M_TRY(all_to_all<T>(c, s.pack, s.spectrum_t, chunk));  // chunk p = planes of rank p: [kx, ky_local, z]
   phase_end(c, PH_COMM);
-  phase_begin(c, PH_FFT_FWD);
-  P3M_FFT(exec_c2c(s.plan_z, s.spectrum_t, CUFFT_FORWARD));
-  c->launches++;
-  phase_end(c, PH_FFT_FWD);
-  phase_begin(c, PH_MULTIPLY);
-  k_multiply_t<<<grid, 256, 0, c->stream>>>(s.spectrum_t, s.green, spec);
-  P3M_LAUNCH_CHECK(c);
-  phase_end(c, PH_MULTIPLY);
-  phase_begin(c, PH_FFT_INV);
-  P3M_FFT(exec_c2c(s.plan_z, s.spectrum_t, CUFFT_INVERSE));
-  c->launches++;
-  phase_end(c, PH_FFT_INV);
+  if (c->fused_z) {
+    phase_begin(c, PH_MULTIPLY);  // forward z FFT + multiply + inverse z FFT in one pass (poisson_z.cu)
+    P3M_TRY(fused_z_pass<T>(c, s.spectrum_t, s.green, (long long)nxh * nyl));
+    phase_end(c, PH_MULTIPLY);
+  } else {
+    phase_begin(c, PH_FFT_FWD);
+    P3M_FFT(exec_c2c(s.plan_z, s.spectrum_t, CUFFT_FORWARD));
+    c->launches++;
+    phase_end(c, PH_FFT_FWD);
+    phase_begin(c, PH_MULTIPLY);
+    k_multiply_t<<<grid, 256, 0, c->stream>>>(s.spectrum_t, s.green, spec);
+    P3M_LAUNCH_CHECK(c);
+    phase_end(c, PH_MULTIPLY);
+    phase_begin(c, PH_FFT_INV);
+    P3M_FFT(exec_c2c(s.plan_z, s.spectrum_t, CUFFT_INVERSE));
+    c->launches++;
+    phase_end(c, PH_FFT_INV);
+  }
   phase_begin(c, PH_COMM);
   P3M_TRY(all_to_all<T>(c, s.spectrum_t, s.pack, chunk));  // chunk p of the transposed array = planes of rank p
   phase_end(c, PH_COMM);
   phase_begin(c, PH_FFT_INV);
   k_transpose_pack<cplx, false><<<grid, 256, 0, c->stream>>>(s.spectrum, s.pack, nxh, g.ny, nyl, nzl);
   P3M_LAUNCH_CHECK(c);
-  P3M_FFT(exec_c2r(s.plan_inv, s.spectrum, s.potential));
-  c->launches += 2;
+  for (int z = 0; z < nzl; z += s.fft_chunk) {
+    P3M_FFT(exec_c2r(s.plan_inv, s.spectrum + splane * z, s.potential + plane * z));
+    c->launches += 2;
+  }
   phase_end(c, PH_FFT_INV);
   return 0;
 }

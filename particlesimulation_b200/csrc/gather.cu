@@ -205,7 +205,10 @@ template <int FD>
 struct PmTile {
   static constexpr int TX = 16, TY = 16, TZ = 8;
   static constexpr int HALO = 1 + FD;  // assignment stencil reach + finite-difference reach
-  static constexpr int PX = TX + 2 * HALO, PY = TY + 2 * HALO, PZ = TZ + 2 * HALO;
+  // row pitch 24 = 8 mod 16: the 4 rows of 8 cells that 32 consecutive sorted particles cover (sub key =
+  // mesh cell, x fastest, inside an 8^3 binning cell) fall into 4 disjoint groups of 8 banks
+  static constexpr int PX = 24, PY = TY + 2 * HALO, PZ = TZ + 2 * HALO;
+  static constexpr int WX = TX + 2 * HALO;  // staged extent in x (<= PX)
   static constexpr int ELEMS = PX * PY * PZ;
 };
 constexpr int kGatherPmDirect = 48;  // blocks with fewer particles read the potential straight from L2
@@ -244,19 +247,24 @@ k_gather_pm(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start, 
   const int ox = ((int)compact3((uint32_t)c0) << kPmTileShift) - TL::HALO;
   const int oy = ((int)compact3((uint32_t)c0 >> 1) << kPmTileShift) - TL::HALO;
   const int oz = ((int)compact3((uint32_t)c0 >> 2) << kPmTileShift) - TL::HALO;
+  // first particle of this thread: in flight while the tile is staged
+  int i = my0 + tid;
+  V4<T> pn = i < my1 ? posm[i] : V4<T>{0, 0, 0, 0};
   for (int el = tid; el < TL::ELEMS; el += 256) {
     const int iz = el / (TL::PX * TL::PY), r = el - iz * (TL::PX * TL::PY);
     const int iy = r / TL::PX, ix = r - iy * TL::PX;
+    if (ix >= TL::WX) continue;  // pitch padding
     const int gx = wrap_idx(ox + ix, g.nx), gy = wrap_idx(oy + iy, g.ny), gz = pot_plane(g, oz + iz);
     sphi[el] = gz < 0 ? T(0) : phi[(long long)gx + (long long)gy * g.nx + (long long)gz * g.nx * g.ny];
   }
   __syncthreads();
   constexpr int SY = TL::PX, SZ = TL::PX * TL::PY;
-  for (int i = my0 + tid; i < my1; i += 256) {
-    const V4<T> p = posm[i];
+  for (; i < my1; i += 256) {
+    const V4<T> p = pn;
+    if (i + 256 < my1) pn = posm[i + 256];  // register prefetch of the next particle
     const Stencil<T, K> st = make_stencil<T, K>(p.x, p.y, p.z, p.w);
     const int rx = st.x0 - ox, ry = st.y0 - oy, rz = st.z0 - oz;
-    const bool fits = rx >= FD && ry >= FD && rz >= FD && rx + K + FD <= TL::PX && ry + K + FD <= TL::PY &&
+    const bool fits = rx >= FD && ry >= FD && rz >= FD && rx + K + FD <= TL::WX && ry + K + FD <= TL::PY &&
                       rz + K + FD <= TL::PZ && st.x0 >= 0 && st.y0 >= 0 && st.z0 >= 0 &&
                       st.x0 + K <= g.nx && st.y0 + K <= g.ny && st.z0 + K <= g.nz;
     T ax = 0, ay = 0, az = 0;

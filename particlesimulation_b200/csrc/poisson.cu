@@ -258,6 +258,15 @@ static cufftResult exec_fwd(cufftHandle p, double* in, cufftDoubleComplex* out) 
 static cufftResult exec_inv(cufftHandle p, cufftComplex* in, float* out) { return cufftExecC2R(p, in, out); }
 static cufftResult exec_inv(cufftHandle p, cufftDoubleComplex* in, double* out) { return cufftExecZ2D(p, in, out); }
 
+// planes per batched 2-D transform: small enough that the intermediate of cuFFT's two passes stays in L2
+int fft_chunk_planes(long long plane_bytes, int planes) {
+  long long budget = 24ll << 20;
+  if (const char* e = getenv("P3M_TUNE_FFT_CHUNK_MB")) budget = atoll(e) << 20;
+  int cp = 1;
+  while (cp * 2 <= planes && (long long)(cp * 2) * plane_bytes <= budget && planes % (cp * 2) == 0) cp *= 2;
+  return cp;
+}
+
 template <typename T>
 int alloc_meshes(p3m_ctx* c) {
   State<T>& s = Sel<T>::st(c);
@@ -266,6 +275,8 @@ int alloc_meshes(p3m_ctx* c) {
   const long long hc = half_count(p);
   // several ranks: slab-decomposed mesh whenever the planes and the ky rows divide evenly
   c->slab = c->nranks > 1 && p.nz % c->nranks == 0 && p.ny % c->nranks == 0 && !getenv("P3M_REPLICATED_MESH");
+  c->fused_z = fused_z_supported(p.nz) && !getenv("P3M_TUNE_CUFFT_Z");
+  if (c->fused_z) P3M_TRY(fused_z_init<T>(c));
   if (c->slab) {
     P3M_TRY(slab_setup<T>(c));
   } else {
@@ -278,9 +289,17 @@ int alloc_meshes(p3m_ctx* c) {
     P3M_CUDA(cudaMemsetAsync(s.density, 0, sizeof(T) * (size_t)g.M, c->stream));
     P3M_CUDA(cudaMemsetAsync(s.potential, 0, sizeof(T) * (size_t)g.M, c->stream));
     const bool dbl = sizeof(T) == 8;
-    // adapters get dims {Nz, Ny, Nx} (source/demos.cpp:758-759): x is the fastest axis
-    P3M_FFT(cufftPlan3d(&s.plan_fwd, p.nz, p.ny, p.nx, dbl ? CUFFT_D2Z : CUFFT_R2C));
-    P3M_FFT(cufftPlan3d(&s.plan_inv, p.nz, p.ny, p.nx, dbl ? CUFFT_Z2D : CUFFT_C2R));
+    if (c->fused_z) {
+      // batched 2-D transforms of the planes; the z leg is k_poisson_z
+      s.fft_chunk = fft_chunk_planes((long long)(p.nx / 2 + 1) * p.ny * sizeof(typename State<T>::cplx), p.nz);
+      int n2[2] = {p.ny, p.nx};
+      P3M_FFT(cufftPlanMany(&s.plan_fwd, 2, n2, nullptr, 1, 0, nullptr, 1, 0, dbl ? CUFFT_D2Z : CUFFT_R2C, s.fft_chunk));
+      P3M_FFT(cufftPlanMany(&s.plan_inv, 2, n2, nullptr, 1, 0, nullptr, 1, 0, dbl ? CUFFT_Z2D : CUFFT_C2R, s.fft_chunk));
+    } else {
+      // adapters get dims {Nz, Ny, Nx} (source/demos.cpp:758-759): x is the fastest axis
+      P3M_FFT(cufftPlan3d(&s.plan_fwd, p.nz, p.ny, p.nx, dbl ? CUFFT_D2Z : CUFFT_R2C));
+      P3M_FFT(cufftPlan3d(&s.plan_inv, p.nz, p.ny, p.nx, dbl ? CUFFT_Z2D : CUFFT_C2R));
+    }
     s.plans = true;
     P3M_FFT(cufftSetStream(s.plan_fwd, c->stream));
     P3M_FFT(cufftSetStream(s.plan_inv, c->stream));
@@ -305,6 +324,27 @@ int poisson(p3m_ctx* c) {
   if (c->slab) {
     P3M_TRY(slab_poisson<T>(c));
     P3M_TRY(slab_spread_potential<T>(c));
+    c->have_potential = true;
+    return 0;
+  }
+  if (c->fused_z) {
+    const p3m_params& p = c->prm;
+    const size_t plane = (size_t)p.nx * p.ny, splane = (size_t)(p.nx / 2 + 1) * p.ny;
+    phase_begin(c, PH_FFT_FWD);
+    for (int z = 0; z < p.nz; z += s.fft_chunk) {
+      P3M_FFT(exec_fwd(s.plan_fwd, s.density + plane * z, s.spectrum + splane * z));
+      c->launches += 2;
+    }
+    phase_end(c, PH_FFT_FWD);
+    phase_begin(c, PH_MULTIPLY);  // forward z FFT + multiply + inverse z FFT
+    P3M_TRY(fused_z_pass<T>(c, s.spectrum, s.green, (long long)splane));
+    phase_end(c, PH_MULTIPLY);
+    phase_begin(c, PH_FFT_INV);
+    for (int z = 0; z < p.nz; z += s.fft_chunk) {
+      P3M_FFT(exec_inv(s.plan_inv, s.spectrum + splane * z, s.potential + plane * z));
+      c->launches += 2;
+    }
+    phase_end(c, PH_FFT_INV);
     c->have_potential = true;
     return 0;
   }

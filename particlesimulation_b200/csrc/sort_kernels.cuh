@@ -7,9 +7,13 @@
 namespace p3m {
 
 // ---- A0: sort keys ---------------------------------------------------------------------------------
-template <typename T>
+// KeyT = uint64_t: (Morton(cell), sub-cell, particle id) -- the order is a pure function of positions and ids.
+// KeyT = uint32_t (PM-only contexts): (Morton(tile), mesh cell in the tile) without the id; the radix sort
+// is stable, so ties keep their previous relative order (id order right after an upload).  Half the key
+// bytes and 4 instead of 7 radix passes on a 512^3 mesh.
+template <typename T, typename KeyT>
 __global__ void k_keys(const V4<T>* __restrict__ posm, const int* __restrict__ id, long long n,
-                       Geom<T> g, uint64_t* __restrict__ keys, uint32_t* __restrict__ slots,
+                       Geom<T> g, KeyT* __restrict__ keys, uint32_t* __restrict__ slots,
                        int* __restrict__ flags) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -34,7 +38,10 @@ __global__ void k_keys(const V4<T>* __restrict__ posm, const int* __restrict__ i
     sx = min(max(sx, 0), S - 1), sy = min(max(sy, 0), S - 1), sz = min(max(sz, 0), S - 1);
     m = (m << (3 * g.sbits)) | morton3((uint32_t)sx, (uint32_t)sy, (uint32_t)sz);
   }
-  keys[i] = (m << g.idbits) | (uint64_t)(uint32_t)id[i];
+  if (sizeof(KeyT) == 8)
+    keys[i] = (KeyT)((m << g.idbits) | (uint64_t)(uint32_t)id[i]);
+  else
+    keys[i] = (KeyT)m;
   slots[i] = (uint32_t)i;
 }
 
@@ -52,7 +59,8 @@ __global__ void k_permute(const uint32_t* __restrict__ slots, long long n,
 }
 
 // cell_start[c] = first sorted slot whose cell code is >= c (lower bound), c in [0, ncells]
-static __global__ void k_cell_start(const uint64_t* __restrict__ keys, long long n, int idbits,
+template <typename KeyT>
+static __global__ void k_cell_start(const KeyT* __restrict__ keys, long long n, int idbits,
                              long long ncells, int* __restrict__ cell_start) {
   long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (c > ncells) return;

@@ -537,3 +537,85 @@ def test_p3m_edge_inputs():
     assert np.isfinite(acc).all()
     assert np.array_equal(sr[0], sr[1])  # coincident particles feel the same force, none from each other
     assert sr[2, 0] < 0 < sr[0, 0]       # attraction along x between the pair and the third particle
+
+
+# ------------------------------------------------------------------------ round-1 additions (kernels)
+@pytest.mark.parametrize("precision", [capi.F32, capi.F64])
+@pytest.mark.parametrize("nz", [16, 32, 64, 128, 256, 512, 1024])
+def test_fused_z_pass_matches_cufft_z_leg(nz, precision, monkeypatch):
+    """k_poisson_z (forward z FFT + influence-function multiply + inverse z FFT in one pass, every radix
+    plan 2^4..2^10) against the all-cuFFT 3-D transform + multiply kernel on the same density."""
+    grid = (8, 4, nz)
+    box = (60.0, 30.0, 60.0 * nz / 8)
+    p = refapi.make_params(16, grid, box, gfunc=refapi.DISCRETE_LAPLACIAN)
+    rng = np.random.default_rng(nz)
+    rho = rng.standard_normal((nz, grid[1], grid[0])).astype(np.float32)
+    out = {}
+    for mode in ("fused", "cufft"):
+        if mode == "cufft":
+            monkeypatch.setenv("P3M_TUNE_CUFFT_Z", "1")
+        else:
+            monkeypatch.delenv("P3M_TUNE_CUFFT_Z", raising=False)
+        with capi.Context(to_p3m(p, p3m=False, precision=precision)) as ctx:
+            ctx.green_init()
+            ctx.set_density(rho)
+            ctx.poisson()
+            out[mode] = ctx.potential(f64=True)
+    monkeypatch.delenv("P3M_TUNE_CUFFT_Z", raising=False)
+    tol = 2e-6 if precision == capi.F32 else 1e-13
+    assert rel_l2(out["fused"], out["cufft"]) < tol
+
+
+def test_short_range_with_unequal_masses_uses_the_general_kernel():
+    """Every sampler of the reference hands out equal masses (folded into the force table); unequal masses
+    take the per-pair mass multiply.  Both against the fp64 oracle, and against each other."""
+    p, pos, vel, mass = plummer_case(6000)
+    rng = np.random.default_rng(3)
+    mass2 = (mass * rng.uniform(0.5, 1.5, mass.shape)).astype(np.float32)
+    o = oracle("f64")
+    res = {}
+    for name, m in (("equal", mass), ("unequal", mass2)):
+        pc, _, mcode = o.to_code_units(p, pos, vel, m)
+        sr_ref = o.sr_forces(p, pc, mcode) / mcode[:, None]
+        with capi.Context(to_p3m(p, p3m=True)) as ctx:
+            ctx.set_particles(pos, vel, m)
+            ctx.bin_sort()
+            ctx.short_range()
+            _, sr = ctx.acc_parts()
+        assert rel_l2(sr, sr_ref) < 2e-5, name
+        res[name] = sr
+    # one particle 1 ulp heavier switches the kernel, not the physics
+    mass3 = mass.copy()
+    mass3[17] = np.nextafter(mass3[17], np.float32(1))
+    with capi.Context(to_p3m(p, p3m=True)) as ctx:
+        ctx.set_particles(pos, vel, mass3)
+        ctx.bin_sort()
+        ctx.short_range()
+        _, sr3 = ctx.acc_parts()
+    assert rel_l2(sr3, res["equal"]) < 1e-6
+
+
+def test_pm_short_key_sort_stays_sorted_over_steps():
+    """PM-only contexts sort on (tile, mesh cell) without the id: after any number of steps the particles
+    are a permutation in non-decreasing key order, and two identical runs give the identical order."""
+    p, pos, vel, mass = uniform_case(20000, gfunc=0)
+    rng = np.random.default_rng(5)
+    vel = (0.4 * rng.standard_normal(vel.shape)).astype(np.float32)
+    orders = []
+    for _ in range(2):
+        with capi.Context(to_p3m(p, p3m=False)) as ctx:
+            ctx.set_particles(pos, vel, mass)
+            ctx.force()
+            ctx.kick(0.5)
+            ctx.step(4)
+            ctx.bin_sort()
+            mc, _, order = ctx.cells()
+            gpos, _, _ = ctx.get_particles(capi.UNITS_CODE)
+        assert np.array_equal(np.sort(order), np.arange(len(mass)))
+        t = gpos.astype(np.int32)
+        key = (morton3(t[:, 0] >> 3, t[:, 1] >> 3, t[:, 2] >> 3) << np.uint64(9)) | \
+              ((t[:, 2] & 7).astype(np.uint64) << np.uint64(6)) | ((t[:, 1] & 7).astype(np.uint64) << np.uint64(3)) | \
+              (t[:, 0] & 7).astype(np.uint64)
+        assert np.all(np.diff(key[order].astype(np.int64)) >= 0)
+        orders.append(order)
+    assert np.array_equal(orders[0], orders[1])
