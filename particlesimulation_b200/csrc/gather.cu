@@ -213,91 +213,143 @@ struct PmTile {
 };
 constexpr int kGatherPmDirect = 48;  // blocks with fewer particles read the potential straight from L2
 
+// non-empty 16 x 16 x 8 blocks (4 consecutive binning cells), compacted
+__global__ void k_occupied_blocks(const int* __restrict__ cell_start, long long ncells, int* __restrict__ list,
+                                  int* __restrict__ counter) {
+  const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (4 * b >= ncells) return;
+  const long long c1 = 4 * b + 4 < ncells ? 4 * b + 4 : ncells;
+  if (cell_start[c1] > cell_start[4 * b]) list[atomicAdd(counter, 1)] = (int)b;
+}
+
+// 4-byte asynchronous copy global -> shared (LDGSTS): no register staging, completes in the background
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Persistent CTAs walk the compacted block list with a static stride.  While a block's particles are
+// interpolated from one shared-memory buffer, the potential tile of the CTA's NEXT block streams into the
+// other buffer with asynchronous copies (periodic wrap applied per element), and the list / cell_start
+// entries of the block after that are already in flight: no global-memory latency sits on the critical path.
 template <typename T, int K, int FD>
 __global__ void __launch_bounds__(256, 3)
-k_gather_pm(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start, Geom<T> g,
-            const T* __restrict__ phi, V4<T>* __restrict__ acc) {
+k_gather_pm(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start, const int* __restrict__ list,
+            const int* __restrict__ counter, Geom<T> g, const T* __restrict__ phi, V4<T>* __restrict__ acc) {
   using TL = PmTile<FD>;
+  static_assert(sizeof(T) == 4 || sizeof(T) == 8, "");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* sphi = reinterpret_cast<T*>(smem_raw);
+  T* const sbuf0 = reinterpret_cast<T*>(smem_raw);
   const int tid = threadIdx.x;
   const long long ncells = 1LL << (3 * g.mbits);
-  const long long c0 = 4LL * blockIdx.x;
-  const int s = cell_start[c0], e = cell_start[c0 + 4 < ncells ? c0 + 4 : ncells];
-  const int count = e - s;
-  if (count <= 0) return;
-  // large blocks (clustered sets) are split over blockIdx.y
-  int per = (count + (int)gridDim.y - 1) / (int)gridDim.y;
-  per = max(2048, (per + 255) & ~255);
-  const int my0 = s + (int)blockIdx.y * per, my1 = min(e, my0 + per);
-  if (my0 >= my1) return;
+  const int nocc = *counter, G = gridDim.x;
   const T scale = (K == 3) ? T(0.125) : T(1);
-  if (count < kGatherPmDirect) {
-    for (int i = my0 + tid; i < my1; i += 256) {
-      const V4<T> p = posm[i];
+  constexpr int SY = TL::PX, SZ = TL::PX * TL::PY;
+
+  auto origin = [&](int blk, int& ox, int& oy, int& oz) {
+    const uint32_t c0 = 4u * (uint32_t)blk;
+    ox = ((int)compact3(c0) << kPmTileShift) - TL::HALO;
+    oy = ((int)compact3(c0 >> 1) << kPmTileShift) - TL::HALO;
+    oz = ((int)compact3(c0 >> 2) << kPmTileShift) - TL::HALO;
+  };
+  auto stage_async = [&](int blk, T* dst) {
+    int ox, oy, oz;
+    origin(blk, ox, oy, oz);
+    for (int el = tid; el < TL::ELEMS; el += 256) {
+      const int iz = el / (TL::PX * TL::PY), r = el - iz * (TL::PX * TL::PY);
+      const int iy = r / TL::PX, ix = r - iy * TL::PX;
+      if (ix >= TL::WX) continue;  // pitch padding
+      const int gx = wrap_idx(ox + ix, g.nx), gy = wrap_idx(oy + iy, g.ny), gz = pot_plane(g, oz + iz);
+      if (gz < 0) {
+        dst[el] = T(0);
+      } else {
+        const T* src = phi + ((long long)gx + (long long)gy * g.nx + (long long)gz * g.nx * g.ny);
+        if (sizeof(T) == 4) {
+          cp_async_4(dst + el, src);
+        } else {
+          cp_async_4(reinterpret_cast<float*>(dst + el), reinterpret_cast<const float*>(src));
+          cp_async_4(reinterpret_cast<float*>(dst + el) + 1, reinterpret_cast<const float*>(src) + 1);
+        }
+      }
+    }
+  };
+  auto range_of = [&](int blk, int& s, int& e) {
+    const long long c0 = 4LL * blk;
+    s = cell_start[c0], e = cell_start[c0 + 4 < ncells ? c0 + 4 : ncells];
+  };
+
+  int w = blockIdx.x;
+  if (w >= nocc) return;
+  int blk = list[w];
+  int blk_n = w + G < nocc ? list[w + G] : -1;
+  int s, e;
+  range_of(blk, s, e);
+  stage_async(blk, sbuf0);
+  cp_async_commit();
+  for (int it = 0; w < nocc; w += G, ++it) {
+    T* sphi = sbuf0 + (it & 1) * TL::ELEMS;
+    // next block: its tile starts streaming now; the block after that is looked up for the next iteration
+    int s_n = 0, e_n = 0;
+    const int blk_nn = w + 2 * G < nocc ? list[w + 2 * G] : -1;
+    if (blk_n >= 0) {
+      range_of(blk_n, s_n, e_n);
+      stage_async(blk_n, sbuf0 + ((it & 1) ^ 1) * TL::ELEMS);
+    }
+    cp_async_commit();
+    int i = s + tid;
+    V4<T> pn = i < e ? posm[i] : V4<T>{0, 0, 0, 0};
+    cp_async_wait<1>();  // everything but the newest group: this block's tile has landed
+    __syncthreads();
+    int ox, oy, oz;
+    origin(blk, ox, oy, oz);
+    const bool direct = e - s < kGatherPmDirect;  // too few particles to be worth a tile: straight from L2
+    for (; i < e; i += 256) {
+      const V4<T> p = pn;
+      if (i + 256 < e) pn = posm[i + 256];  // register prefetch of the next particle
       const Stencil<T, K> st = make_stencil<T, K>(p.x, p.y, p.z, p.w);
+      const int rx = st.x0 - ox, ry = st.y0 - oy, rz = st.z0 - oz;
+      const bool fits = !direct && rx >= FD && ry >= FD && rz >= FD && rx + K + FD <= TL::WX &&
+                        ry + K + FD <= TL::PY && rz + K + FD <= TL::PZ && st.x0 >= 0 && st.y0 >= 0 && st.z0 >= 0 &&
+                        st.x0 + K <= g.nx && st.y0 + K <= g.ny && st.z0 + K <= g.nz;
       T ax = 0, ay = 0, az = 0;
-      gather_direct<T, K, FD>(st, g, phi, ax, ay, az);
+      if (fits) {
+        const T* base = sphi + (rz * TL::PY + ry) * TL::PX + rx;
+#pragma unroll
+        for (int a = 0; a < K; ++a)
+#pragma unroll
+          for (int b = 0; b < K; ++b)
+#pragma unroll
+            for (int cc = 0; cc < K; ++cc) {
+              const T* q = base + (cc * TL::PY + b) * TL::PX + a;
+              if (FD == 1) {
+                const T wgt = (st.wx[a] * st.wy[b]) * st.wz[cc];
+                ax += wgt * (q[1] - q[-1]), ay += wgt * (q[SY] - q[-SY]), az += wgt * (q[SZ] - q[-SZ]);
+              } else {
+                const T wgt = scale * ((st.wx[a] * st.wy[b]) * st.wz[cc]);
+                const T k = T(-1.0) / 12;
+                ax += wgt * (k * (-q[2] + 8 * q[1] - 8 * q[-1] + q[-2]));
+                ay += wgt * (k * (-q[2 * SY] + 8 * q[SY] - 8 * q[-SY] + q[-2 * SY]));
+                az += wgt * (k * (-q[2 * SZ] + 8 * q[SZ] - 8 * q[-SZ] + q[-2 * SZ]));
+              }
+            }
+        if (FD == 1) {
+          const T f = T(-0.5) * scale;
+          ax *= f, ay *= f, az *= f;
+        }
+      } else {
+        gather_direct<T, K, FD>(st, g, phi, ax, ay, az);
+      }
       add_external(g, p.x, p.y, p.z, ax, ay, az);
       acc[i] = V4<T>{ax, ay, az, 0};
     }
-    return;
+    __syncthreads();  // this buffer is overwritten by the copies issued in the next iteration
+    blk = blk_n, blk_n = blk_nn, s = s_n, e = e_n;
   }
-  // first staged mesh index on each axis
-  const int ox = ((int)compact3((uint32_t)c0) << kPmTileShift) - TL::HALO;
-  const int oy = ((int)compact3((uint32_t)c0 >> 1) << kPmTileShift) - TL::HALO;
-  const int oz = ((int)compact3((uint32_t)c0 >> 2) << kPmTileShift) - TL::HALO;
-  // first particle of this thread: in flight while the tile is staged
-  int i = my0 + tid;
-  V4<T> pn = i < my1 ? posm[i] : V4<T>{0, 0, 0, 0};
-  for (int el = tid; el < TL::ELEMS; el += 256) {
-    const int iz = el / (TL::PX * TL::PY), r = el - iz * (TL::PX * TL::PY);
-    const int iy = r / TL::PX, ix = r - iy * TL::PX;
-    if (ix >= TL::WX) continue;  // pitch padding
-    const int gx = wrap_idx(ox + ix, g.nx), gy = wrap_idx(oy + iy, g.ny), gz = pot_plane(g, oz + iz);
-    sphi[el] = gz < 0 ? T(0) : phi[(long long)gx + (long long)gy * g.nx + (long long)gz * g.nx * g.ny];
-  }
-  __syncthreads();
-  constexpr int SY = TL::PX, SZ = TL::PX * TL::PY;
-  for (; i < my1; i += 256) {
-    const V4<T> p = pn;
-    if (i + 256 < my1) pn = posm[i + 256];  // register prefetch of the next particle
-    const Stencil<T, K> st = make_stencil<T, K>(p.x, p.y, p.z, p.w);
-    const int rx = st.x0 - ox, ry = st.y0 - oy, rz = st.z0 - oz;
-    const bool fits = rx >= FD && ry >= FD && rz >= FD && rx + K + FD <= TL::WX && ry + K + FD <= TL::PY &&
-                      rz + K + FD <= TL::PZ && st.x0 >= 0 && st.y0 >= 0 && st.z0 >= 0 &&
-                      st.x0 + K <= g.nx && st.y0 + K <= g.ny && st.z0 + K <= g.nz;
-    T ax = 0, ay = 0, az = 0;
-    if (fits) {
-      const T* base = sphi + (rz * TL::PY + ry) * TL::PX + rx;
-#pragma unroll
-      for (int a = 0; a < K; ++a)
-#pragma unroll
-        for (int b = 0; b < K; ++b)
-#pragma unroll
-          for (int cc = 0; cc < K; ++cc) {
-            const T* q = base + (cc * TL::PY + b) * TL::PX + a;
-            if (FD == 1) {
-              const T w = (st.wx[a] * st.wy[b]) * st.wz[cc];
-              ax += w * (q[1] - q[-1]), ay += w * (q[SY] - q[-SY]), az += w * (q[SZ] - q[-SZ]);
-            } else {
-              const T w = scale * ((st.wx[a] * st.wy[b]) * st.wz[cc]);
-              const T k = T(-1.0) / 12;
-              ax += w * (k * (-q[2] + 8 * q[1] - 8 * q[-1] + q[-2]));
-              ay += w * (k * (-q[2 * SY] + 8 * q[SY] - 8 * q[-SY] + q[-2 * SY]));
-              az += w * (k * (-q[2 * SZ] + 8 * q[SZ] - 8 * q[-SZ] + q[-2 * SZ]));
-            }
-          }
-      if (FD == 1) {
-        const T f = T(-0.5) * scale;
-        ax *= f, ay *= f, az *= f;
-      }
-    } else {
-      gather_direct<T, K, FD>(st, g, phi, ax, ay, az);
-    }
-    add_external(g, p.x, p.y, p.z, ax, ay, az);
-    acc[i] = V4<T>{ax, ay, az, 0};
-  }
+  cp_async_wait<0>();
 }
 
 template <typename T, int K, int FD>
@@ -305,14 +357,16 @@ static int launch_gather_pm(p3m_ctx* c) {
   State<T>& s = Sel<T>::st(c);
   const Geom<T>& g = Sel<T>::g(c);
   const long long ncells = 1LL << (3 * g.mbits);
-  const unsigned blocks = (unsigned)((ncells + 3) / 4);
-  // one CTA per block; a block holding very many particles (a clustered set in a PM-only run) is walked
-  // by its CTA in passes of 256.  gridDim.y is the hook for splitting such blocks.
-  const int split = 1;
+  const long long nblocks = (ncells + 3) / 4;
+  int* list = s.pp_items + ncells;  // free in PM-only contexts (first ncells entries: deposit's cell list)
+  int* counter = s.pp_counters + 7;
+  P3M_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), c->stream));
+  k_occupied_blocks<<<(unsigned)((nblocks + 255) / 256), 256, 0, c->stream>>>(s.cell_start, ncells, list, counter);
+  P3M_LAUNCH_CHECK(c);
   auto kern = k_gather_pm<T, K, FD>;
-  const size_t smem = sizeof(T) * PmTile<FD>::ELEMS;
+  const size_t smem = 2 * sizeof(T) * PmTile<FD>::ELEMS;
   P3M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<dim3(blocks, split), 256, smem, c->stream>>>(s.posm, s.cell_start, g, s.pot_part, s.acc);
+  kern<<<c->num_sms * 3, 256, smem, c->stream>>>(s.posm, s.cell_start, list, counter, g, s.pot_part, s.acc);
   P3M_LAUNCH_CHECK(c);
   return 0;
 }

@@ -258,9 +258,11 @@ static cufftResult exec_fwd(cufftHandle p, double* in, cufftDoubleComplex* out) 
 static cufftResult exec_inv(cufftHandle p, cufftComplex* in, float* out) { return cufftExecC2R(p, in, out); }
 static cufftResult exec_inv(cufftHandle p, cufftDoubleComplex* in, double* out) { return cufftExecZ2D(p, in, out); }
 
-// planes per batched 2-D transform: small enough that the intermediate of cuFFT's two passes stays in L2
+// planes per batched 2-D transform.  Measured on B200 (512^3): splitting the batch so that the intermediate of
+// cuFFT's two passes would stay in L2 is SLOWER than one batch over all planes (2.39 vs 1.73 ms per solve),
+// so the default is one batch; P3M_TUNE_FFT_CHUNK_MB re-enables the split for measurements.
 int fft_chunk_planes(long long plane_bytes, int planes) {
-  long long budget = 24ll << 20;
+  long long budget = 1ll << 60;
   if (const char* e = getenv("P3M_TUNE_FFT_CHUNK_MB")) budget = atoll(e) << 20;
   int cp = 1;
   while (cp * 2 <= planes && (long long)(cp * 2) * plane_bytes <= budget && planes % (cp * 2) == 0) cp *= 2;
