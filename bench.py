@@ -110,7 +110,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.time()] + [x.strip() for x in line.split(",")])
+
+    def mark(self):
+        """Start of the timed region: the sampler itself is started earlier (nvidia-smi takes ~0.5 s to
+        deliver its first line), samples taken before the mark are dropped."""
+        self.t0 = time.time()
 
     def stop(self):
         if not self.proc:
@@ -121,7 +126,11 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        t0 = getattr(self, "t0", 0.0)
+        rows = [r[1:] for r in self.rows if r[0] >= t0]
+        if not rows and self.rows:  # region shorter than one sampling period: nearest sample
+            rows = [self.rows[-1][1:]]
+        for r in rows:
             if len(r) < 7:
                 continue
             try:
@@ -168,6 +177,28 @@ def multi_params(capi, world, timing=False):
     p = c2_params(capi, timing)
     p.nz = GRID_C2[2] * world
     p.box[2] = BOX_C2[2] * world
+    return p
+
+
+def c4_params(capi, grid, timing=False):
+    """BASELINE.json configs[3]: P3M on a grid^3 mesh (1024 on 8 GPUs), TSC, S1-optimal influence function,
+    a = 3H, re = 0.7a, the softening of C2 in mesh units."""
+    f32 = np.float32
+    p = capi.default_params()
+    p.nx = p.ny = p.nz = grid
+    p.box[:] = BOX_C2
+    p.H = f32(f32(BOX_C2[0]) / f32(grid // 2))
+    p.DT, p.G = 1.0, 4.5e-3
+    p.assignment, p.fd_scheme, p.greens_function = capi.TSC, capi.TWO_POINT, capi.S1_OPTIMAL
+    p.particle_diameter = f32(f32(3) * f32(p.H))
+    p.p3m = 1
+    p.cutoff_radius = f32(f32(0.7) * f32(p.particle_diameter))
+    p.softening = f32(0.5 * float(p.H) / (60.0 / 64.0))
+    p.cloud_shape, p.use_sr_table = capi.S1, 1
+    p.precision = capi.F32
+    p.unit_roundtrip = 1
+    p.green_zero_degenerate = 1
+    p.timing = int(timing)
     return p
 
 
@@ -391,13 +422,14 @@ def run_ours(args):
     ctx.kick(0.5)  # setHalfStepVelocities
     flush_bytes = 256 << 20
     flush = cu.malloc(flush_bytes)
+    clocks = ClockSampler(0)
+    clocks.start()
     for _ in range(args.warmup):
         ctx.step(1)
     ev = [(cu.event(), cu.event()) for _ in range(args.steps)]
     launches0 = ctx.launches
-    clocks = ClockSampler(0)
-    clocks.start()
     cu.sync()
+    clocks.mark()
     t_wall0 = time.time()
     for a, b in ev:
         cu.check(cu.rt.cudaMemsetAsync(flush, 0, flush_bytes, stream), "flush")  # evict L2 (126 MB)
@@ -514,10 +546,24 @@ def run_ours_multi(args, rank, world, local):
     assert world == args.gpus, f"WORLD_SIZE {world} != --gpus {args.gpus}"
     cu = Cuda()
     cu.set_device(local)
-    n_per = int(os.environ.get("P3M_BENCH_N", N_C2))
-    pos, vel, mass = multi_particles(world, n_per)
-    n_total = len(mass)
-    prm = multi_params(capi, world)
+    c4 = args.config == "c4"
+    if c4:
+        from particlesimulation_b200 import ics
+        n_total = int(os.environ.get("P3M_BENCH_N", 1 << 26))
+        grid = int(os.environ.get("P3M_BENCH_GRID", 1024))
+        pos, vel, mass = ics.clustered_disk_halo(n_total, seed=42)
+        prm = c4_params(capi, grid)
+        workload = (f"C4: P3M clustered disk + halo, {n_total} particles, {grid}^3 mesh, TSC, S1-optimal Green, "
+                    f"chaining-mesh PP (re=0.7a, a=3H), strong scaling over {world} GPUs")
+        mesh = [grid, grid, grid]
+    else:
+        n_per = int(os.environ.get("P3M_BENCH_N", N_C2))
+        pos, vel, mass = multi_particles(world, n_per)
+        n_total = len(mass)
+        prm = multi_params(capi, world)
+        workload = (f"C5-style weak scaling of C2: one P3M Plummer sphere of 2^20 particles per GPU, "
+                    f"mesh 128x128x{128 * world}, TSC, S1-optimal Green, chaining-mesh PP")
+        mesh = [GRID_C2[0], GRID_C2[1], GRID_C2[2] * world]
     prm.device = local
     ctx = pdist.create_context(prm, capi)
     stream = ctx.stream
@@ -525,17 +571,18 @@ def run_ours_multi(args, rank, world, local):
     ctx.green_init()
     ctx.force()
     ctx.kick(0.5)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     for _ in range(args.warmup):
         ctx.step(1)
     flush_bytes = 256 << 20
     flush = cu.malloc(flush_bytes)
     ev = [(cu.event(), cu.event()) for _ in range(args.steps)]
     launches0 = ctx.launches
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     dist.barrier()
     cu.sync()
+    clocks.mark()
     for a, b in ev:
         cu.check(cu.rt.cudaMemsetAsync(flush, 0, flush_bytes, stream), "flush")
         cu.record(a, stream)
@@ -580,15 +627,35 @@ def run_ours_multi(args, rank, world, local):
     e2e_s = float(te.item()) / e2e_steps
     tb = torch.tensor([float(h2d), float(d2h)], device="cuda")
     dist.all_reduce(tb)
+    extra = {}
+    if c4:
+        # phase breakdown (max over ranks) and exact pair statistics from a timing context
+        ctx.close()
+        tprm = c4_params(capi, grid, timing=True)
+        tprm.device = local
+        ctx = pdist.create_context(tprm, capi)
+        ctx.set_particles(pos, vel, mass)
+        ctx.green_init(); ctx.force(); ctx.kick(0.5); ctx.step(1)
+        ctx.phase_ms(reset=True)
+        ctx.step(2)
+        ph = ctx.phase_ms()
+        names = sorted(ph)
+        tp = torch.tensor([ph[k] / 2 for k in names], device="cuda")
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        checked, inside = ctx.pair_counts()
+        pc = torch.tensor([float(checked), float(inside)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(pc)
+        extra = {"ms_per_step_by_phase_max_over_ranks": dict(zip(names, [round(float(x), 3) for x in tp.tolist()])),
+                 "pairs_in_range_per_particle": float(pc[1].item()) / n_total,
+                 "pairs_checked_per_particle": float(pc[0].item()) / n_total}
     if rank == 0:
         value = n_total * args.steps / (total_ms / 1e3)
         line = {
             "metric": "P3M particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C5-style weak scaling of C2: one P3M Plummer sphere of 2^20 particles per GPU, "
-                                   f"mesh 128x128x{128 * world}, TSC, S1-optimal Green, chaining-mesh PP",
-                       "particles": n_total, "mesh": [GRID_C2[0], GRID_C2[1], GRID_C2[2] * world],
+            "higher_is_better": True, "scaling": "strong" if c4 else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload, "particles": n_total, "mesh": mesh, **extra,
                        "l2": "256 MiB memset between timed steps (outside the events)",
                        "parallelism": f"z-slabs of particles over {world} GPUs; NCCL over NVLink: migration, ghost layers, density/"
                                       f"potential plane exchange, slab-decomposed FFT with all-to-all transpose "
@@ -614,8 +681,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="c2", choices=["c2", "mesh"],
-                    help="c2 = the headline workload; mesh = secondary mesh-dominated PM run (1 GPU)")
+    ap.add_argument("--config", default="c2", choices=["c2", "mesh", "c4"],
+                    help="c2 = the headline workload; mesh = secondary mesh-dominated PM run; c4 = BASELINE configs[3] "
+                         "(P3M clustered disk+halo, 2^26 particles, 1024^3 mesh; torchrun, 8 GPUs)")
     args = ap.parse_args()
     if args.impl == "reference":
         if int(os.environ.get("RANK", 0)) != 0:

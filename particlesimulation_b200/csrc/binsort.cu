@@ -8,6 +8,7 @@
 // records, so every cell is a contiguous, id-ordered slice of the particle arrays.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -119,8 +120,12 @@ int upload_particles(p3m_ctx* c, const float* pos, const float* vel, const float
     if (units == P3M_UNITS_ORIGINAL) m = mf * m;
     c->uniform_mass_code = (double)m;
   }
-  // multi-GPU: every rank was handed the whole set; keep the particles of this rank's z-slab
-  if (c->nranks > 1) P3M_TRY(dist_migrate<T>(c, false));
+  // multi-GPU: every rank was handed the whole set; balance the layer cuts on it (identically on every rank),
+  // then keep the particles of this rank's z-slab
+  if (c->nranks > 1) {
+    P3M_TRY(dist_balance_cuts<T>(c, pos, n, units));
+    P3M_TRY(dist_migrate<T>(c, false));
+  }
   return 0;
 }
 

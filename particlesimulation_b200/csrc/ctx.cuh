@@ -54,8 +54,9 @@ struct State {
   bool plan_z_made = false;
   // short range
   T* sr_table = nullptr;  // 2*kSRTable: (F[t], F[t+1]-F[t]) pairs; entry 499 = (0,0)
-  int* pp_items = nullptr;     // (cell, first target) pairs for the tiled kernel
-  int* pp_counters = nullptr;  // [0] items, [1] next item, [2] flags
+  int* pp_items = nullptr;     // (cell, first target) pairs of the dense-cell kernel; PM-only contexts: the
+                               // occupied-cell / occupied-block lists of deposit and gather
+  int* pp_counters = nullptr;  // [0] items, [1] next item, [4] escape probe, [6] / [7] list lengths (PM)
   unsigned long long* pair_counts = nullptr;  // [0] checked, [1] in range
   int* flags = nullptr;    // [0] escaped, [1] out-of-mesh particles seen
   double* diag = nullptr;  // 16 doubles
@@ -185,6 +186,9 @@ int fft_chunk_planes(long long plane_bytes, int planes);
 // dist_mesh.cu: slab-decomposed mesh
 template <typename T> int slab_setup(p3m_ctx* c);             // after dist_init: plane ranges, buffers, plans
 template <typename T> void slab_free(p3m_ctx* c);
+template <typename T> int slab_replan(p3m_ctx* c);           // after the layer cuts moved
+// dist.cu: equal-COUNT layer cuts from the full particle set every rank was handed (clustered sets)
+template <typename T> int dist_balance_cuts(p3m_ctx* c, const float* pos, long long n, int units);
 template <typename T> int slab_reduce_density(p3m_ctx* c);    // dens_part of all ranks -> density slabs
 template <typename T> int slab_poisson(p3m_ctx* c);           // distributed FFT Poisson solve
 template <typename T> int slab_spread_potential(p3m_ctx* c);  // potential slabs -> pot_part of all ranks

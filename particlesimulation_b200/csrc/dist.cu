@@ -22,7 +22,10 @@
 
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "ctx.cuh"
 #include "sort_kernels.cuh"
@@ -61,6 +64,87 @@ static void set_cuts(p3m_ctx* c) {
   g.lay0 = g.cut[c->rank];
   g.lay1 = c->rank == P - 1 ? 0x7fffffff : g.cut[c->rank + 1];
   if (c->rank == 0) g.lay0 = -0x7fffffff;
+}
+
+// Balanced cuts.  p3m_set_particles hands every rank the SAME full particle set, so every rank computes the same
+// per-layer weights on the host and the same cuts -- nothing is communicated.
+//   PM-only:  weight of a binning layer = its particle count (mesh kernels are linear in the particles);
+//   P3M:      + the short-range work of the layer: sum over its chaining cells of n_cell * (particles in the
+//             27-cell neighbourhood), i.e. the pair evaluations the gather-form PP kernels will make; a particle
+//             is charged as kPairsPerParticle pair evaluations of mesh-side work.
+// cut[r] = first layer at which the cumulative weight reaches r/P of the total, kept strictly increasing so that
+// every rank owns at least one layer.  A single layer is never split, so a structure thinner than one layer
+// along z still lands on one rank.
+template <typename T>
+int dist_balance_cuts(p3m_ctx* c, const float* pos, long long n, int units) {
+  if (c->nranks <= 1 || n <= 0 || getenv("P3M_STATIC_CUTS")) return 0;
+  Geom<T>& g = Sel<T>::g(c);
+  const int P = c->nranks;
+  set_cuts<T>(c);  // geometric cuts: defines the number of layers being cut
+  const int layers = g.cut[P];
+  const double kPairsPerParticle = 300.0;
+  const double h[3] = {g.p3m ? (double)g.hcx : (double)(1 << g.tile_shift),
+                       g.p3m ? (double)g.hcy : (double)(1 << g.tile_shift),
+                       g.p3m ? (double)g.hcz : (double)(1 << g.tile_shift)};
+  const double u = units == P3M_UNITS_ORIGINAL ? 1.0 / (double)c->prm.H : 1.0;
+  const double inv[3] = {u / h[0], u / h[1], u / h[2]};
+  std::vector<double> weight((size_t)layers, 0.0);
+  auto clampi = [](int v, int hi) { return v < 0 ? 0 : (v >= hi ? hi - 1 : v); };
+  if (!g.p3m || getenv("P3M_COUNT_CUTS")) {
+    for (long long i = 0; i < n; ++i)
+      weight[(size_t)clampi((int)std::floor((double)pos[3 * i + 2] * inv[2]), layers)] += 1.0;
+  } else {
+    const int mx = g.mx, my = g.my;
+    const size_t plane = (size_t)mx * my, cells = plane * (size_t)layers;
+    std::vector<unsigned> cnt(cells, 0u), sx(cells), sy(cells);
+    for (long long i = 0; i < n; ++i) {
+      const int x = clampi((int)std::floor((double)pos[3 * i] * inv[0]), mx);
+      const int y = clampi((int)std::floor((double)pos[3 * i + 1] * inv[1]), my);
+      const int z = clampi((int)std::floor((double)pos[3 * i + 2] * inv[2]), layers);
+      cnt[(size_t)z * plane + (size_t)y * mx + x]++;
+    }
+    // separable 3 x 3 x 3 box sum (non-periodic, like the chaining mesh)
+    for (size_t r = 0; r < cells; r += mx)
+      for (int x = 0; x < mx; ++x)
+        sx[r + x] = cnt[r + x] + (x > 0 ? cnt[r + x - 1] : 0u) + (x + 1 < mx ? cnt[r + x + 1] : 0u);
+    for (int z = 0; z < layers; ++z)
+      for (int y = 0; y < my; ++y) {
+        const size_t r = (size_t)z * plane + (size_t)y * mx;
+        for (int x = 0; x < mx; ++x)
+          sy[r + x] = sx[r + x] + (y > 0 ? sx[r + x - mx] : 0u) + (y + 1 < my ? sx[r + x + mx] : 0u);
+      }
+    for (int z = 0; z < layers; ++z) {
+      double w = 0.0;
+      for (size_t k = 0; k < plane; ++k) {
+        const size_t i = (size_t)z * plane + k;
+        if (!cnt[i]) continue;
+        const double s27 = (double)sy[i] + (z > 0 ? (double)sy[i - plane] : 0.0) + (z + 1 < layers ? (double)sy[i + plane] : 0.0);
+        w += (double)cnt[i] * (kPairsPerParticle + s27);
+      }
+      weight[(size_t)z] = w;
+    }
+  }
+  double total = 0.0;
+  for (double w : weight) total += w;
+  int cut[9];
+  cut[0] = 0;
+  double cum = 0.0;
+  int l = 0;
+  for (int r = 1; r < P; ++r) {
+    const double want = total * r / P;
+    while (l < layers && cum + weight[(size_t)l] <= want) cum += weight[(size_t)l++];
+    // the layer holding the quantile goes to whichever side leaves the smaller excess
+    int k = l;
+    if (l < layers && want - cum > cum + weight[(size_t)l] - want) k = l + 1;
+    if (k <= cut[r - 1]) k = cut[r - 1] + 1;
+    if (k > layers - (P - r)) k = layers - (P - r);
+    cut[r] = k;
+  }
+  for (int r = P; r <= 8; ++r) cut[r] = layers;
+  for (int r = 0; r <= 8; ++r) g.cut[r] = cut[r];
+  g.lay0 = c->rank == 0 ? -0x7fffffff : g.cut[c->rank];
+  g.lay1 = c->rank == P - 1 ? 0x7fffffff : g.cut[c->rank + 1];
+  return slab_replan<T>(c);
 }
 
 void dist_set_cuts(p3m_ctx* c) {
@@ -376,6 +460,8 @@ int dist_ghosts(p3m_ctx* c) {
   return 0;
 }
 
+template int dist_balance_cuts<float>(p3m_ctx*, const float*, long long, int);
+template int dist_balance_cuts<double>(p3m_ctx*, const float*, long long, int);
 template int dist_migrate<float>(p3m_ctx*, bool);
 template int dist_migrate<double>(p3m_ctx*, bool);
 template int dist_ghosts<float>(p3m_ctx*);

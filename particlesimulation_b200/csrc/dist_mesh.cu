@@ -131,6 +131,36 @@ void slab_free(p3m_ctx* c) {
   s.plan_z_made = false;
 }
 
+// The layer cuts changed (dist_balance_cuts): re-derive the plane ranges of the particle-side buffers and
+// re-allocate them.  The FFT slabs themselves never move.
+template <typename T>
+int slab_replan(p3m_ctx* c) {
+  if (!c->slab) return 0;
+  State<T>& s = Sel<T>::st(c);
+  Geom<T>& g = Sel<T>::g(c);
+  const int me = c->rank;
+  const size_t plane = (size_t)g.nx * g.ny;
+  const int old_den = c->den_nz[me], old_pot = c->pot_nz[me];
+  plane_ranges<T>(c);
+  g.den_off = (long long)c->den_z0[me] * (long long)plane;
+  g.den_len = (long long)c->den_nz[me] * (long long)plane;
+  g.pot_z0 = c->pot_z0[me], g.pot_nz = c->pot_nz[me];
+  P3M_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->den_nz[me] > old_den) {
+    cudaFree(s.dens_part);
+    s.dens_part = nullptr;
+    P3M_CUDA(cudaMalloc((void**)&s.dens_part, sizeof(T) * plane * (size_t)c->den_nz[me]));
+  }
+  if (c->pot_nz[me] > old_pot) {
+    cudaFree(s.pot_part);
+    s.pot_part = nullptr;
+    P3M_CUDA(cudaMalloc((void**)&s.pot_part, sizeof(T) * plane * (size_t)c->pot_nz[me]));
+  }
+  P3M_CUDA(cudaMemsetAsync(s.pot_part, 0, sizeof(T) * plane * (size_t)c->pot_nz[me], c->stream));
+  c->have_potential = false;
+  return 0;
+}
+
 // Allocates the slab-sized meshes and the three cuFFT plans.  Called instead of the full-mesh allocation.
 template <typename T>
 int slab_setup(p3m_ctx* c) {
@@ -336,6 +366,8 @@ int slab_poisson(p3m_ctx* c) {
   return 0;
 }
 
+template int slab_replan<float>(p3m_ctx*);
+template int slab_replan<double>(p3m_ctx*);
 template void slab_free<float>(p3m_ctx*);
 template void slab_free<double>(p3m_ctx*);
 template int slab_setup<float>(p3m_ctx*);

@@ -309,7 +309,7 @@ int alloc_meshes(p3m_ctx* c) {
   P3M_CUDA(cudaMalloc((void**)&s.cell_start, sizeof(int) * (((size_t)1 << (3 * g.mbits)) + 2)));
   P3M_CUDA(cudaMalloc((void**)&s.sr_table, sizeof(T) * 2 * kSRTable));
   P3M_CUDA(cudaMalloc((void**)&s.pp_counters, sizeof(int) * 8));
-  P3M_CUDA(cudaMalloc((void**)&s.pair_counts, sizeof(unsigned long long) * 2));
+  P3M_CUDA(cudaMalloc((void**)&s.pair_counts, sizeof(unsigned long long) * 4));  // [2]: estimated dense-cell pairs
   P3M_CUDA(cudaMalloc((void**)&s.flags, sizeof(int) * 4));
   P3M_CUDA(cudaMalloc((void**)&s.diag, sizeof(double) * 16));
   P3M_CUDA(cudaMemsetAsync(s.flags, 0, sizeof(int) * 4, c->stream));

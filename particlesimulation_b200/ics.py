@@ -94,3 +94,53 @@ def uniform_cube(n, lo, hi, total_mass=1.0, seed=42):
     vel = np.zeros((n, 3))
     mass = np.full(n, total_mass / n)
     return pos.astype(np.float32), vel.astype(np.float32), mass.astype(np.float32)
+
+
+def clustered_disk_halo(n, box=60.0, seed=42, halo_a=12.0, halo_rmax=27.0, disk_rd=24.0, thickness=3.0, M=1.0,
+                        G=4.5e-3):
+    """BASELINE.json config 4 ("clustered disk + halo"): half the particles in a disk with linearly
+    decreasing surface density (triangular radial law), half in a Plummer halo of scale `halo_a`, both centred
+    in the box; equal masses.  The disk lies in the x-z plane (normal along y), so the z-slab decomposition of
+    the multi-GPU path cuts through it instead of handing the whole disk to one rank.  float32 throughout and O(10) vectorised passes, so that 2^26 particles are
+    generated in seconds; velocities are circular (disk, from the enclosed mass) / isotropic at half the local
+    escape speed (halo) -- synthetic data for throughput runs, not an equilibrium model."""
+    rng = np.random.default_rng(seed)
+    f32 = np.float32
+    nd = n // 2
+    nh = n - nd
+    c = f32(box / 2)
+    pos = np.empty((n, 3), f32)
+    vel = np.zeros((n, 3), f32)
+    # disk
+    u = rng.random(nd, dtype=f32)
+    r = f32(disk_rd) * (f32(1) - np.sqrt(f32(1) - u))
+    phi = f32(2 * np.pi) * rng.random(nd, dtype=f32)
+    cs, sn = np.cos(phi), np.sin(phi)
+    pos[:nd, 0] = c + r * cs
+    pos[:nd, 2] = c + r * sn
+    pos[:nd, 1] = c + f32(thickness) * (rng.random(nd, dtype=f32) - f32(0.5))
+    menc = f32(M) * (f32(0.5) * (f32(1) - (f32(1) - r / f32(disk_rd)) ** 2) +
+                     f32(0.5) * (r ** 3) / (r * r + f32(halo_a) ** 2) ** f32(1.5))
+    v = np.sqrt(f32(G) * menc / np.maximum(r, f32(1e-3)))
+    vel[:nd, 0] = -v * sn
+    vel[:nd, 2] = v * cs
+    del u, r, phi, cs, sn, menc, v
+    # halo
+    u = np.maximum(rng.random(nh, dtype=f32), f32(1e-7))
+    r = f32(halo_a) / np.sqrt(u ** f32(-2.0 / 3.0) - f32(1))
+    r = np.minimum(r, f32(halo_rmax))
+    cos_t = f32(1) - f32(2) * rng.random(nh, dtype=f32)
+    sin_t = np.sqrt(np.maximum(f32(0), f32(1) - cos_t * cos_t))
+    phi = f32(2 * np.pi) * rng.random(nh, dtype=f32)
+    pos[nd:, 0] = c + r * sin_t * np.cos(phi)
+    pos[nd:, 1] = c + r * sin_t * np.sin(phi)
+    pos[nd:, 2] = c + r * cos_t
+    vesc = np.sqrt(f32(2 * G * M) / np.sqrt(r * r + f32(halo_a) ** 2))
+    cos_t = f32(1) - f32(2) * rng.random(nh, dtype=f32)
+    sin_t = np.sqrt(np.maximum(f32(0), f32(1) - cos_t * cos_t))
+    phi = f32(2 * np.pi) * rng.random(nh, dtype=f32)
+    vel[nd:, 0] = f32(0.5) * vesc * sin_t * np.cos(phi)
+    vel[nd:, 1] = f32(0.5) * vesc * sin_t * np.sin(phi)
+    vel[nd:, 2] = f32(0.5) * vesc * cos_t
+    mass = np.full(n, M / n, f32)
+    return pos, vel, mass
