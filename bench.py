@@ -342,6 +342,23 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
+def profile_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the newest committed
+    `ncu --set full` summary under profiles/ (tools/summarize_ncu.py); None if there is none."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"{kernel}_*.txt")), key=os.path.getmtime)
+    if not files:
+        return None, None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for line in open(files[-1]):
+        m = re.match(r"dram__bytes_(read|write)\.sum\s+([0-9.,]+)\s+(\w+)", line)
+        if m:
+            tot += float(m.group(2).replace(",", "")) * scale.get(m.group(3), 1.0)
+    return (tot if tot > 0 else None), os.path.basename(files[-1])
+
+
 # ------------------------------------------------------------------------------------ reference arm
 def reference_sample_params(n):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -461,7 +478,8 @@ def run_ours(args):
         rc = lib.p3m_get_particles(ctx._h, op.ctypes.data_as(C.c_void_p), ov.ctypes.data_as(C.c_void_p), None,
                                    capi.UNITS_ORIGINAL)  # D2H: pos, vel (24 B / particle)
         assert rc == 0
-        hp[:], hv[:] = op, ov
+        hp, op = op, hp                         # the caller's next step starts from what came back
+        hv, ov = ov, hv
     e2e_s = (time.time() - t0) / e2e_steps
     e2e_value = n / e2e_s
 
@@ -500,7 +518,8 @@ def run_ours(args):
     }
     roofline = {"kernel": "k_pp_tiled (short-range PP, dense chaining cells)", "bound": "fp32",
                 "achieved": pp_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": pp_tflops / fp32_peak if fp32_peak else None, "traffic": None,
+                "frac": pp_tflops / fp32_peak if fp32_peak else None, "traffic": profile_traffic("k_pp_tiled")[0],
+                "traffic_source": f"dram bytes read + written per launch, ncu --set full capture profiles/{profile_traffic('k_pp_tiled')[1]}",
                 "peak_source": f"148 SMs x 128 FP32 lanes x 2 flop x clocks.max.sm {sm_max:.0f} MHz (no tensor cores on "
                                f"this path; HBM peak for the other kernels: {peak_src})",
                 "flops_per_launch": pp_flops, "pairs_checked": checked, "pairs_in_range": inside,

@@ -2,19 +2,21 @@
 // (source/pmMethod.cpp:200-277, source/grid.cpp:28-36).
 //
 // The reference takes one std::mutex per touched cell (27 lock/unlock pairs per TSC particle); its
-// CUDA mirror issues 27 global float atomics per particle (source/PMMethodGPU.cu:312-336).  Here the
-// particles arrive cell-sorted, so a WARP owns a run of consecutive particles and accumulates them
-// into a private shared-memory tile (the mesh footprint of one aligned block of binning cells):
-//   * sm_100a has no native shared-memory float add (atomicAdd on __shared__ float compiles to an
-//     ATOMS.CAST.SPIN loop), so the tile is updated with plain LDS/FADD/STS; exclusivity inside the
-//     warp is established per batch of 32 particles with match.any on the particle's base cell:
-//       - all lanes in one cell (dense cores): the 27 contributions are summed across the warp with
-//         shuffles and written once (warp-aggregated);
-//       - otherwise lanes sharing a cell take turns (rank rounds); for one stencil point, distinct base
-//         cells mean distinct addresses, so each round is conflict free;
-//   * the tile is flushed once per segment with native REDG.ADD (fp32 and fp64) to the global mesh,
-//     skipping zeros;
-//   * runs too short to amortise a tile (sparse outskirts) go straight to global REDG.
+// CUDA mirror issues 27 global float atomics per particle (source/PMMethodGPU.cu:312-336).  sm_100a has no
+// native shared-memory float add (atomicAdd on __shared__ float compiles to an ATOMS.CAST.SPIN loop), so
+// both kernels here get exclusivity from the work assignment and update shared-memory tiles with plain
+// LDS / FADD / STS; tiles are flushed to the global mesh with native REDG.ADD (fp32 and fp64), zeros skipped.
+//   k_deposit_pm  PM-only contexts, CIC / TSC: one thread per mesh cell, register accumulation, TMA
+//                 bulk-copy double buffering (see the comment above the kernel);
+//   k_deposit     P3M contexts and NGP: a WARP owns a run of consecutive sorted particles and a private tile
+//                 (the mesh footprint of one aligned block of binning cells).  Per batch of 32 particles the
+//                 lanes sharing a base cell are found with match.any:
+//                   - all lanes in one cell (dense cores): the 27 contributions are summed across the warp
+//                     with shuffles and written once (warp-aggregated);
+//                   - otherwise the lowest lane of each group pulls the other members through shuffles and
+//                     sums their stencils in registers, so ONE round of read-modify-writes serves the batch
+//                     (leaders hold distinct cells, hence distinct addresses per stencil point);
+//                 runs too short to amortise a tile (sparse outskirts) go straight to global REDG.
 // Algorithmic HBM traffic: 16 B/particle read + 4 B/cell written (+ 4 B/cell memset).
 #include <cstdlib>
 

@@ -14,23 +14,23 @@
 //
 //   dense cells (>= kDenseCell particles; the Plummer core puts ~half of all particles in 8 cells):
 //     work item = (cell, 64 consecutive targets) handled by ONE WARP, 2 targets per lane in registers.
-//     Particles are sorted by (cell, 8^3 sub-cell, id), so 64 consecutive particles are spatially
-//     compact; every globally aligned 64-particle group carries a bounding box (k_tile_aabb) and a
-//     source group whose box is farther than the cutoff from the box of the warp's targets is skipped
-//     WHOLE (exact: it only drops pairs with r >= re).  Surviving groups are staged in the warp's
-//     private shared-memory slice (next one prefetched in registers) and read back with broadcast
-//     LDS.128; there is no block-wide barrier in the loop.  Items are generated on the device, sorted
-//     by cost (heaviest first) and pulled from an atomic queue by a persistent grid.
+//     Particles are sorted by (cell, 16^3 sub-cell, id), so consecutive particles are spatially compact;
+//     every globally aligned 32-particle group carries a bounding box (k_tile_aabb) and a source group whose
+//     box is farther than the cutoff from the box of the warp's targets is skipped WHOLE (exact: it only
+//     drops pairs with r >= re).  Surviving groups are staged in the warp's private shared-memory slice
+//     (next one prefetched in registers) and read back with broadcast LDS.128; there is no block-wide
+//     barrier in the loop.  Items are generated on the device, sorted by cost (heaviest first) and pulled
+//     from an atomic queue by a persistent grid.
 //   sparse cells: one thread per target walks its 27 cells straight from L1/L2.
 //
-// Force law (code units, G = 1/(4 pi)): table mode reproduces shortRangeForceFromTable
-// (:240-245): linear interpolation in r^2 over 500 entries, multiplied by r_ij (NOT the unit vector,
-// SURVEY Q7).  Inner loop, per pair: 3 FADD (d: exact for close pairs, as in the reference), FMUL +
-// 2 FFMA (r^2), FMUL (xi = r^2 / delta^2), FMNMX (clamp to 499: entry 499 is (0,0), which folds the
-// cutoff test r^2 >= re^2 of :258 into the lookup), FADD.RZ with 2^23 (floor(xi) lands in the
-// mantissa), LEA, LDS.64 of (A_t, B_t) = (F_t - t dF_t, dF_t), FFMA (f = A + B xi), FMUL (mj), 3 FFMA
-// (accumulate) = 16 issue slots.  r = 0 contributes exactly 0 (F_0 = 0), so i == j needs no test.
-// Bound: FP32 / issue rate, not memory.
+// Force law (code units, G = 1/(4 pi)): table mode reproduces shortRangeForceFromTable (:240-245): linear
+// interpolation in r^2 over 500 entries, multiplied by r_ij (NOT the unit vector).  Coordinates
+// are staged in units of the cutoff, so u = |d|^2 = r^2 / re^2 saturates to 1 exactly at the cutoff, where
+// the last table entry is (0, 0): that folds the test r^2 < re^2 of :258 into the lookup.  Inner loop, per
+// pair: 3 FADD (d), FMUL + FFMA + FFMA.SAT (u), FFMA.RZ with 2^23 (floor(499 u) lands in the mantissa), LEA,
+// LDS.64 of (A_t, B_t) from the lane's conflict-free copy of the table, FFMA (f = A + B u), 3 FFMA
+// (accumulate) = 13 issue slots with equal masses (+1 FMUL otherwise).  r = 0 contributes exactly 0
+// (F_0 = 0), so i == j needs no test.  Bound: FP32 / issue rate, not memory.
 #include <cub/device/device_radix_sort.cuh>
 
 #include <cmath>
