@@ -82,7 +82,11 @@ int dist_balance_cuts(p3m_ctx* c, const float* pos, long long n, int units) {
   const int P = c->nranks;
   set_cuts<T>(c);  // geometric cuts: defines the number of layers being cut
   const int layers = g.cut[P];
-  const double kPairsPerParticle = 300.0;
+  // mesh-side work of one particle in units of one pair evaluation (sort + deposit + gather + integrate ~0.15-0.5
+  // ns vs ~0.5-1 ps per pair on B200).  A caller that re-uploads all particles every step (bench.py's e2e loop)
+  // is transfer-bound instead and wants a much larger value: P3M_TUNE_PARTICLE_WEIGHT overrides it.
+  double kPairsPerParticle = 300.0;
+  if (const char* e = getenv("P3M_TUNE_PARTICLE_WEIGHT")) kPairsPerParticle = atof(e);
   const double h[3] = {g.p3m ? (double)g.hcx : (double)(1 << g.tile_shift),
                        g.p3m ? (double)g.hcy : (double)(1 << g.tile_shift),
                        g.p3m ? (double)g.hcz : (double)(1 << g.tile_shift)};
