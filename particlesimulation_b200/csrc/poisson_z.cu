@@ -111,13 +111,22 @@ __device__ __forceinline__ int slot_index(int t, int u, int r) {
   return t + u * (N / 8) + r * (N / R);
 }
 
-template <typename T, int N, int P, int R>
+// Shared-memory slot of element `pos` of column c.  The lanes of a warp hold C columns x 32/C consecutive
+// threads t, whose elements are either consecutive (stride 1) or R0 = 8 apart (store of the first stage);
+// row pos lives at row pos + pos/8, so both patterns walk through consecutive rows of C words and a warp
+// covers 32 distinct banks (a plain odd pitch left 43 % of the wavefronts as conflicts, ncu r01n).
+template <int C>
+__device__ __forceinline__ int sidx(int pos, int c) {
+  return (pos + (pos >> 3)) * C + c;
+}
+
+template <typename T, int N, int C, int R>
 __device__ __forceinline__ void stage_load(Cx<T> (&e)[8], const T* re, const T* im, int t, int c) {
 #pragma unroll
   for (int u = 0; u < 8 / R; ++u)
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int pos = slot_index<N, R>(t, u, r) * P + c;
+      const int pos = sidx<C>(slot_index<N, R>(t, u, r), c);
       e[u * R + r] = Cx<T>{re[pos], im[pos]};
     }
 }
@@ -136,7 +145,7 @@ __device__ __forceinline__ void stage_compute(Cx<T> (&e)[8], const Cx<T>* tw, in
   }
 }
 
-template <typename T, int N, int P, int R, int Ns>
+template <typename T, int N, int C, int R, int Ns>
 __device__ __forceinline__ void stage_store(const Cx<T> (&e)[8], T* re, T* im, int t, int c) {
 #pragma unroll
   for (int u = 0; u < 8 / R; ++u) {
@@ -145,7 +154,7 @@ __device__ __forceinline__ void stage_store(const Cx<T> (&e)[8], T* re, T* im, i
     const int j0 = (j - k) * R + k;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int pos = (j0 + r * Ns) * P + c;
+      const int pos = sidx<C>(j0 + r * Ns, c);
       re[pos] = e[u * R + r].x, im[pos] = e[u * R + r].y;
     }
   }
@@ -154,15 +163,15 @@ __device__ __forceinline__ void stage_store(const Cx<T> (&e)[8], T* re, T* im, i
 // stages S .. n-1 of one transform; the first stage starts from registers, the last one ends in registers
 template <typename T, int LOGN, int C, bool INV, int S>
 __device__ __forceinline__ void run_stages(Cx<T> (&e)[8], const Cx<T>* tw, T* re, T* im, int t, int c) {
-  constexpr int N = 1 << LOGN, P = C + 1;
+  constexpr int N = 1 << LOGN;
   constexpr int R = stage_radix<LOGN, INV>(S), Ns = stage_ns<LOGN, INV>(S);
   if (S > 0) {
-    stage_load<T, N, P, R>(e, re, im, t, c);
+    stage_load<T, N, C, R>(e, re, im, t, c);
     __syncthreads();  // everybody has read the previous stage before anyone overwrites it
   }
   stage_compute<T, N, R, Ns>(e, tw, t);
   if constexpr (S < Plan<LOGN>::n - 1) {
-    stage_store<T, N, P, R, Ns>(e, re, im, t, c);
+    stage_store<T, N, C, R, Ns>(e, re, im, t, c);
     __syncthreads();
     run_stages<T, LOGN, C, INV, S + 1>(e, tw, re, im, t, c);
   }
@@ -171,11 +180,11 @@ __device__ __forceinline__ void run_stages(Cx<T> (&e)[8], const Cx<T>* tw, T* re
 template <typename T, int LOGN, int C>
 __global__ void __launch_bounds__(C * (1 << LOGN) / 8)
 k_poisson_z(Cx<T>* __restrict__ spec, const T* __restrict__ green, const Cx<T>* __restrict__ twg, long long ncols) {
-  constexpr int N = 1 << LOGN, P = C + 1;  // odd row pitch: consecutive rows fall into different banks
+  constexpr int N = 1 << LOGN;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Cx<T>* tw = reinterpret_cast<Cx<T>*>(smem_raw);
   T* re = reinterpret_cast<T*>(tw + N);
-  T* im = re + (size_t)N * P;
+  T* im = re + (size_t)(N + N / 8) * C;
   const int c = threadIdx.x % C, t = threadIdx.x / C;
   const long long col = (long long)blockIdx.x * C + c;
   const bool valid = col < ncols;
@@ -233,7 +242,7 @@ template <typename T, int LOGN, int C>
 int launch_z(p3m_ctx* c, void* spec, const T* green, long long ncols) {
   State<T>& s = Sel<T>::st(c);
   constexpr int N = 1 << LOGN;
-  const size_t smem = sizeof(Cx<T>) * (size_t)N + 2 * sizeof(T) * (size_t)N * (C + 1);
+  const size_t smem = sizeof(Cx<T>) * (size_t)N + 2 * sizeof(T) * (size_t)(N + N / 8) * C;
   auto kern = k_poisson_z<T, LOGN, C>;
   P3M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long blocks = (ncols + C - 1) / C;
