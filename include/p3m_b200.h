@@ -113,6 +113,12 @@ int64_t p3m_num_global(const p3m_ctx* ctx);
 /* host-only: the binning layers along z and their cuts for `nranks` ranks (cuts[r]..cuts[r+1] belongs to
  * rank r); needs no device, identical on every rank.  layers_out = number of layers that are cut. */
 int p3m_slab_cuts(const p3m_params* params, int nranks, int32_t cuts[9], int32_t* layers_out);
+/* host-only: the WORK-BALANCED cuts p3m_set_particles derives from a full particle set (packed xyz, `units` as
+ * for p3m_set_particles): particle count per layer for PM-only parameters, estimated pair evaluations of the
+ * short-range kernels + particles for P3M.  Deterministic, so every rank computes the same cuts from the same
+ * set without communicating.  Needs no device. */
+int p3m_balanced_cuts(const p3m_params* params, int nranks, const float* pos, int64_t n, int units,
+                      int32_t cuts[9], int32_t* layers_out);
 /* out = {rank, nranks, first owned binning layer, one past the last, ghost particles held,
  *        1 if the mesh is slab-decomposed (distributed FFT) / 0 if replicated, first mesh plane of this
  *        rank's FFT slab, number of planes in it} */

@@ -55,7 +55,7 @@ _lib = None
 SYMBOLS = [
     "p3m_last_error", "p3m_version", "p3m_default_params", "p3m_create", "p3m_destroy",
     "p3m_comm_unique_id", "p3m_create_dist", "p3m_get_local", "p3m_set_particles_ids", "p3m_num_global",
-    "p3m_rank_info", "p3m_slab_cuts",
+    "p3m_rank_info", "p3m_slab_cuts", "p3m_balanced_cuts",
     "p3m_set_particles", "p3m_get_particles", "p3m_get_particles_f64", "p3m_num_particles",
     "p3m_green_init", "p3m_set_green_table", "p3m_set_green_table_f64", "p3m_get_green_table",
     "p3m_bin_sort", "p3m_deposit", "p3m_poisson", "p3m_gradient", "p3m_gather", "p3m_short_range",
@@ -134,6 +134,16 @@ def slab_cuts(params, nranks):
     cuts = np.zeros(9, np.int32)
     layers = C.c_int32(0)
     _check(lib().p3m_slab_cuts(C.byref(params), int(nranks), _p(cuts), C.byref(layers)))
+    return cuts[: nranks + 1].copy(), int(layers.value)
+
+
+def balanced_cuts(params, nranks, pos, units=UNITS_ORIGINAL):
+    """Work-balanced layer cuts for a full particle set (host only; what p3m_set_particles uses on N ranks)."""
+    pos = np.ascontiguousarray(pos, np.float32)
+    cuts = np.zeros(9, np.int32)
+    layers = C.c_int32(0)
+    _check(lib().p3m_balanced_cuts(C.byref(params), int(nranks), _p(pos), C.c_int64(len(pos)), int(units), _p(cuts),
+                                   C.byref(layers)))
     return cuts[: nranks + 1].copy(), int(layers.value)
 
 

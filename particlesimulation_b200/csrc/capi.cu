@@ -222,6 +222,26 @@ int p3m_slab_cuts(const p3m_params* prm, int nranks, int32_t cuts[9], int32_t* l
   return 0;
 }
 
+int p3m_balanced_cuts(const p3m_params* prm, int nranks, const float* pos, int64_t n, int units, int32_t cuts[9],
+                      int32_t* layers_out) {
+  if (!prm || !cuts || nranks < 1 || nranks > 8 || n < 0 || (n > 0 && !pos))
+    return fail(P3M_EINVAL, "p3m_balanced_cuts: bad argument");
+  p3m_ctx c;
+  c.prm = *prm;
+  c.f64 = false;
+  c.rank = 0, c.nranks = nranks;
+  int r = setup_geometry<float>(&c);
+  if (r != 0) return r;
+  dist_set_cuts(&c);
+  if (c.g32.cut[nranks] < nranks)
+    return fail(P3M_EINVAL, "only %d binning layers along z for %d ranks", c.g32.cut[nranks], nranks);
+  r = dist_balance_cuts<float>(&c, pos, (long long)n, units);  // host arithmetic only (no slab buffers here)
+  if (r != 0) return r;
+  for (int i = 0; i < 9; ++i) cuts[i] = c.g32.cut[i];
+  if (layers_out) *layers_out = c.g32.cut[nranks];
+  return 0;
+}
+
 int p3m_comm_unique_id(void* out) {
   if (!out) return fail(P3M_EINVAL, "null output");
   return comm_unique_id(out);

@@ -33,6 +33,14 @@ mine = int((owner == rank).sum())
 tot = torch.tensor([mine]); dist.all_reduce(tot)
 assert int(tot) == len(mass), "every particle must have exactly one owner"
 assert abs(mine - len(mass) / world) < 0.05 * len(mass), "clusters are one per slab"
+# work-balanced cuts: every rank derives them from the full set it was handed, without communication
+bc, _ = capi.balanced_cuts(prm, world, pos)
+tb = torch.tensor(bc.tolist()); gb = [torch.zeros_like(tb) for _ in range(world)]
+dist.all_gather(gb, tb)
+assert all(torch.equal(g, tb) for g in gb), "balanced cuts differ between ranks"
+owner_b = pdist.owner_of(pos[:, 2] / np.float32(prm.H), bc, hc)
+tot_b = torch.tensor([int((owner_b == rank).sum())]); dist.all_reduce(tot_b)
+assert int(tot_b) == len(mass), "balanced cuts must partition the set exactly once"
 dist.barrier()
 if rank == 0: print("DIST_CPU_OK")
 dist.destroy_process_group()
