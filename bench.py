@@ -621,25 +621,33 @@ def run_ours_multi(args, rank, world, local):
     dist.all_reduce(nmax, op=dist.ReduceOp.MAX)
 
     # end to end: every rank uploads the particles it holds (pinned host buffers, explicit ids), steps,
-    # and reads them back
-    ids, lp, lv, _ = ctx.get_local(capi.UNITS_ORIGINAL)
+    # and reads them back into the other set of pinned buffers (ping-pong: no host-side copies in the loop)
+    cap_h = int(1.25 * max(ctx.n, n_total // world)) + 4096
+    bufs = [(cu.pinned((cap_h,), np.int32), cu.pinned((cap_h, 3)), cu.pinned((cap_h, 3))) for _ in range(2)]
+    hm = cu.pinned((cap_h,))
+    equal_mass = bool(mass.min() == mass.max())
+    hm[:] = mass[0]  # equal masses (the samplers' M / n): no per-step gather; else refreshed from the ids below
+    ids, lp, lv, _ = ctx.get_local(capi.UNITS_ORIGINAL, out=bufs[0])
     nl = len(ids)
-    hp, hv, hm = cu.pinned((nl + 4096, 3)), cu.pinned((nl + 4096, 3)), cu.pinned((nl + 4096,))
-    hid = cu.pinned((nl + 4096,), np.int32)
-    hp[:nl], hv[:nl], hm[:nl], hid[:nl] = lp, lv, mass[ids], ids
     e2e_steps = max(2, min(args.steps, 5))
     h2d = d2h = 0
     t0 = None
+    cur = 0
     for it in range(e2e_steps + 1):
         if it == 1:
             dist.barrier(); cu.sync(); t0 = time.time(); h2d = d2h = 0
+        hid, hp, hv = bufs[cur]
+        if not equal_mass:
+            hm[:nl] = mass[hid[:nl]]
         ctx.set_particles_ids(hp[:nl], hv[:nl], hm[:nl], hid[:nl])
         h2d += 32 * nl
         ctx.step(1)
-        ids, lp, lv, _ = ctx.get_local(capi.UNITS_ORIGINAL)
-        nl = min(len(ids), hp.shape[0])
+        if ctx.n > cap_h:
+            raise RuntimeError("end-to-end buffers too small for this rank's share")
+        ids, lp, lv, _ = ctx.get_local(capi.UNITS_ORIGINAL, out=bufs[cur ^ 1])
+        nl = len(ids)
         d2h += 28 * nl
-        hp[:nl], hv[:nl], hm[:nl], hid[:nl] = lp[:nl], lv[:nl], mass[ids[:nl]], ids[:nl]
+        cur ^= 1
     cu.sync(); dist.barrier()
     te = torch.tensor([time.time() - t0], device="cuda")
     dist.all_reduce(te, op=dist.ReduceOp.MAX)

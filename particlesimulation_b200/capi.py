@@ -217,8 +217,15 @@ class Context:
         return dict(zip(("rank", "nranks", "layer0", "layer1", "ghosts", "slab", "plane0", "planes"),
                         (int(v) for v in d)))
 
-    def get_local(self, units=UNITS_ORIGINAL, want=("pos", "vel")):
+    def get_local(self, units=UNITS_ORIGINAL, want=("pos", "vel"), out=None):
+        """This rank's particles with their global ids.  `out` = (ids, pos, vel) preallocated (e.g. pinned)
+        arrays of at least self.n rows: filled in place, views of the first n rows returned."""
         n = self.n
+        if out is not None:
+            ids, pos, vel = out
+            assert len(ids) >= n and len(pos) >= n and len(vel) >= n
+            _check(lib().p3m_get_local(self._h, _p(ids), _p(pos), _p(vel), None, units))
+            return ids[:n], pos[:n], vel[:n], None
         ids = np.empty(n, np.int32)
         out = {k: (np.empty((n, 3), np.float32) if k in want else None) for k in ("pos", "vel", "acc")}
         _check(lib().p3m_get_local(self._h, _p(ids), _p(out["pos"]), _p(out["vel"]), _p(out["acc"]), units))
