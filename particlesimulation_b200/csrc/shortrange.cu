@@ -193,7 +193,14 @@ __global__ void k_pp_items(const int* __restrict__ cell_start, Geom<T> g, int* _
 template <typename T>
 struct PPCfg {
   static constexpr int kCopies = 128 / (2 * (int)sizeof(T));  // conflict-free table replication
-  static constexpr int kWarps = 16;                            // warps per CTA
+#ifndef P3M_PP_WARPS
+#define P3M_PP_WARPS 16
+#endif
+#ifndef P3M_PP_UNROLL
+#define P3M_PP_UNROLL 8
+#endif
+  static constexpr int kWarps = P3M_PP_WARPS;                  // warps per CTA
+  static constexpr int kUnroll = P3M_PP_UNROLL;                // sources per unrolled inner-loop body
   static constexpr int kCtasPerSm = sizeof(T) == 8 ? 1 : 2;
   static constexpr size_t smem(int sub) {
     return sizeof(T) * 2 * kSRTable * kCopies + sizeof(T) * 4 * (size_t)sub * kWarps + 128;
@@ -322,7 +329,7 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
                 if (SUB > 32) n1 = (jb + 32 + lane < je) ? stage(spos[jb + 32 + lane]) : far_;
               }
               if (COUNT) checked += (unsigned long long)cnt * ((v0 ? 1 : 0) + (v1 ? 1 : 0));
-#pragma unroll 8
+#pragma unroll PPCfg<T>::kUnroll
               for (int j = 0; j < cnt; ++j) {
                 const V4<T> sj = s_src[j];
                 unsigned c0 = 0, c1 = 0;
