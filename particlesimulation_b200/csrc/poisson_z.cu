@@ -112,9 +112,11 @@ __device__ __forceinline__ int slot_index(int t, int u, int r) {
 }
 
 // Shared-memory slot of element `pos` of column c.  The lanes of a warp hold C columns x 32/C consecutive
-// threads t, whose elements are either consecutive (stride 1) or R0 = 8 apart (store of the first stage);
-// row pos lives at row pos + pos/8, so both patterns walk through consecutive rows of C words and a warp
-// covers 32 distinct banks (a plain odd pitch left 43 % of the wavefronts as conflicts, ncu r01n).
+// threads t, whose elements are either consecutive (stride 1) or one radix apart (store of a first stage: 8,
+// or 4 when the plan ends in a radix-4 stage, which opens the inverse).  Row pos lives at row pos + pos/8, so
+// strides 1 and 8 walk through consecutive rows of C words and a warp covers 32 distinct banks; stride 4 is
+// left with a 2-way conflict on that one store (tests/test_zpass_model.py enumerates every access).  A plain
+// odd pitch left 43 % of the wavefronts as conflicts (ncu r01n).
 template <int C>
 __device__ __forceinline__ int sidx(int pos, int c) {
   return (pos + (pos >> 3)) * C + c;
