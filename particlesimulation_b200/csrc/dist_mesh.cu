@@ -118,6 +118,20 @@ static void plane_ranges(p3m_ctx* c) {
   }
 }
 
+// planes this rank receives in slab_reduce_density: the overlaps of every OTHER rank's deposit range with
+// my FFT slab.  With work-balanced cuts several thin particle slabs (each with its own halo planes) can sit
+// inside one FFT slab, so this is computed from the ranges instead of bounded by a formula.
+static size_t stage_planes_needed(const p3m_ctx* c, int nzl) {
+  size_t need = 0;
+  for (int p = 0; p < c->nranks; ++p) {
+    if (p == c->rank) continue;
+    const int lo = std::max(c->den_z0[p], c->rank * nzl);
+    const int hi = std::min(c->den_z0[p] + c->den_nz[p], (c->rank + 1) * nzl);
+    if (hi > lo) need += (size_t)(hi - lo);
+  }
+  return need + 1;
+}
+
 template <typename T>
 void slab_free(p3m_ctx* c) {
   State<T>& s = Sel<T>::st(c);
@@ -141,6 +155,7 @@ int slab_replan(p3m_ctx* c) {
   const int me = c->rank;
   const size_t plane = (size_t)g.nx * g.ny;
   const int old_den = c->den_nz[me], old_pot = c->pot_nz[me];
+  const size_t old_stage = stage_planes_needed(c, g.nz / c->nranks);
   plane_ranges<T>(c);
   g.den_off = (long long)c->den_z0[me] * (long long)plane;
   g.den_len = (long long)c->den_nz[me] * (long long)plane;
@@ -155,6 +170,12 @@ int slab_replan(p3m_ctx* c) {
     cudaFree(s.pot_part);
     s.pot_part = nullptr;
     P3M_CUDA(cudaMalloc((void**)&s.pot_part, sizeof(T) * plane * (size_t)c->pot_nz[me]));
+  }
+  const size_t new_stage = stage_planes_needed(c, g.nz / c->nranks);
+  if (new_stage > old_stage) {
+    cudaFree(s.den_stage);
+    s.den_stage = nullptr;
+    P3M_CUDA(cudaMalloc((void**)&s.den_stage, sizeof(T) * plane * new_stage));
   }
   P3M_CUDA(cudaMemsetAsync(s.pot_part, 0, sizeof(T) * plane * (size_t)c->pot_nz[me], c->stream));
   c->have_potential = false;
@@ -179,9 +200,8 @@ int slab_setup(p3m_ctx* c) {
   P3M_CUDA(cudaMalloc((void**)&s.potential, sizeof(T) * plane * nzl));
   P3M_CUDA(cudaMalloc((void**)&s.dens_part, sizeof(T) * plane * (size_t)c->den_nz[me]));
   P3M_CUDA(cudaMalloc((void**)&s.pot_part, sizeof(T) * plane * (size_t)c->pot_nz[me]));
-  // received density planes: every source overlaps my slab with at most nzl planes, all sources together
-  // with at most nzl + 4 planes each side of a cut
-  P3M_CUDA(cudaMalloc((void**)&s.den_stage, sizeof(T) * plane * (size_t)(nzl + 4 * P)));
+  // received density planes (re-sized by slab_replan when the cuts move)
+  P3M_CUDA(cudaMalloc((void**)&s.den_stage, sizeof(T) * plane * stage_planes_needed(c, nzl)));
   P3M_CUDA(cudaMalloc((void**)&s.spectrum, sizeof(cplx) * spec));
   P3M_CUDA(cudaMalloc((void**)&s.spectrum_t, sizeof(cplx) * spec));
   P3M_CUDA(cudaMalloc((void**)&s.pack, sizeof(cplx) * spec));
