@@ -71,6 +71,9 @@ typedef struct p3m_params {
                                 is 0/0 rounding noise there and the mode carries no force */
   int32_t device;            /* CUDA device ordinal; -1 = current device */
   int32_t timing;            /* 1: bracket every phase with CUDA events (p3m_get_phase_ms) */
+  float sr_particle_diameter; /* P3MMethod's own particleDiameter (source/p3mMethod.cpp:36: the cloud size of
+                                the short-range reference force) when it differs from PMMethod's (the cloud
+                                size of the influence function, source/pmMethod.cpp:56); 0 = the same */
 } p3m_params;
 
 typedef struct p3m_ctx p3m_ctx;
@@ -100,6 +103,7 @@ int p3m_destroy(p3m_ctx* ctx);
  * The mesh is slab-decomposed when nz and ny are multiples of nranks; otherwise every rank keeps a full
  * mesh and the density is all-reduced (small meshes only). */
 #define P3M_UNIQUE_ID_BYTES 128
+#define P3M_MAX_RANKS 8   /* one NVSwitch node; larger rank counts are rejected with P3M_EINVAL */
 int p3m_comm_unique_id(void* out_bytes128);
 int p3m_create_dist(const p3m_params* params, const void* unique_id_bytes128, int rank, int nranks,
                     p3m_ctx** out);
@@ -124,7 +128,8 @@ int p3m_balanced_cuts(const p3m_params* params, int nranks, const float* pos, in
  *        rank's FFT slab, number of planes in it} */
 int p3m_rank_info(p3m_ctx* ctx, int64_t out[8]);
 
-/* Particle upload.  units = P3M_UNITS_ORIGINAL applies stateToCodeUnits + massToCodeUnits on the
+/* Particle upload.  The host arrays (pageable or pinned) may be reused as soon as the call returns.
+ * units = P3M_UNITS_ORIGINAL applies stateToCodeUnits + massToCodeUnits on the
  * device (source/unitConversions.cpp:23-71, include/unitConversions.h:8-50), as the head of run()
  * does (source/pmMethod.cpp:72-73).  vel may be NULL (zeros).  Replaces the constructor's copy of
  * `state`/`masses` into vector<Particle> and PMMethodGPU::copyParticlesHostToDevice
@@ -172,7 +177,11 @@ int p3m_short_range(p3m_ctx* ctx);
  * bin_sort, deposit, poisson, gather, short_range. */
 int p3m_force(p3m_ctx* ctx);
 
-/* A10: leapfrog free functions (source/leapfrog.cpp:5-24), code units. */
+/* A10: leapfrog free functions (source/leapfrog.cpp:5-24), code units.
+ * Accelerations belong to the particle order they were computed in: p3m_bin_sort (and a multi-GPU migration)
+ * permutes positions, velocities and ids only, so p3m_kick, p3m_diagnostics and every acceleration readback
+ * return P3M_ESTATE between a re-sort and the next p3m_gather.  p3m_short_range on its own (no p3m_gather
+ * since the sort) starts from zero accelerations. */
 int p3m_kick(p3m_ctx* ctx, float dt_factor);   /* v += dt_factor * a  (0.5 = setHalfStepVelocities) */
 int p3m_drift(p3m_ctx* ctx);                    /* x += v (+ unit round trip, + escape check) */
 /* A11: `steps` iterations of the run-loop body without recording (source/pmMethod.cpp:87-121,
@@ -230,8 +239,21 @@ int p3m_get_sr_table(p3m_ctx* ctx, double* table500);
  * (source/pmMethod.cpp:21-28, source/p3mMethod.cpp:14-17). */
 int p3m_get_phase_ms(p3m_ctx* ctx, float ms[P3M_NPHASE], int reset);
 const char* p3m_phase_name(int i);
-/* exact pair statistics of the last p3m_short_range: pairs examined and pairs within the cutoff */
+/* exact pair statistics of the current (sorted) particle set: pairs examined by the short-range kernels and
+ * pairs within the cutoff.  Runs a counting instantiation of the same kernels that only READS the particle
+ * state (accelerations are not touched) and involves no collective; multi-GPU: this rank's targets only.
+ * Needs sorted particles (P3M_ESTATE otherwise): call it after p3m_short_range / p3m_force / p3m_step. */
 int p3m_get_pair_counts(p3m_ctx* ctx, uint64_t* checked, uint64_t* in_range);
+/* which code paths are active and what the last force evaluation exchanged (this rank's figures):
+ *  [0] fused z pass (k_poisson_z) in use   [1] slab-decomposed mesh   [2] equal-mass table in use
+ *  [3] packed-FP32 dense-cell kernel in use [4] incremental re-sort enabled
+ *  [5] particles this rank sent away in the last migration   [6] ghost particles held
+ *  [7] bytes sent in the two all-to-all transposes of the last solve   [8] density-plane bytes sent
+ *  [9] potential-plane bytes sent   [10] migration bytes sent   [11] ghost bytes sent
+ *  [12] particles that changed cell in the last re-sort (-1: full sort)   [13] full sorts so far
+ *  [14] incremental re-sorts so far   [15] reserved */
+#define P3M_NSTAT 16
+int p3m_get_stats(p3m_ctx* ctx, double out[P3M_NSTAT]);
 /* kernels launched by this context so far (bench.py's gpu_launches) */
 int64_t p3m_launch_count(const p3m_ctx* ctx);
 /* the context's stream as a cudaStream_t, for event timing by the caller */

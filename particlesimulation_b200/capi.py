@@ -40,6 +40,7 @@ class P3MParams(C.Structure):
         ("ext_R", C.c_float), ("ext_M", C.c_float),
         ("precision", C.c_int32), ("unit_roundtrip", C.c_int32),
         ("green_zero_degenerate", C.c_int32), ("device", C.c_int32), ("timing", C.c_int32),
+        ("sr_particle_diameter", C.c_float),
     ]
 
 
@@ -64,7 +65,7 @@ SYMBOLS = [
     "p3m_get_density", "p3m_get_potential", "p3m_get_field", "p3m_get_density_f64",
     "p3m_get_potential_f64", "p3m_set_density", "p3m_set_potential", "p3m_get_cells",
     "p3m_get_chaining_dims", "p3m_get_binning", "p3m_chaining_neighbors", "p3m_get_acc_parts", "p3m_get_sr_table",
-    "p3m_get_phase_ms", "p3m_phase_name", "p3m_get_pair_counts", "p3m_launch_count", "p3m_stream",
+    "p3m_get_phase_ms", "p3m_phase_name", "p3m_get_pair_counts", "p3m_get_stats", "p3m_launch_count", "p3m_stream",
     "p3m_synchronize",
 ]
 
@@ -109,6 +110,7 @@ def lib():
         L.p3m_get_acc_parts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.p3m_get_pair_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.p3m_get_phase_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.p3m_get_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.p3m_chaining_neighbors.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         _lib = L
     return _lib
@@ -353,6 +355,19 @@ class Context:
         a = C.c_uint64(0); b = C.c_uint64(0)
         _check(lib().p3m_get_pair_counts(self._h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
+
+    STAT_NAMES = ("fused_z", "slab", "uniform_mass_table", "packed_pp", "incremental_sort", "migrated", "ghosts",
+                  "a2a_bytes", "density_plane_bytes", "potential_plane_bytes", "migration_bytes", "ghost_bytes",
+                  "sort_movers", "full_sorts", "incremental_sorts", "reserved")
+
+    def stats(self):
+        d = np.zeros(16, np.float64)
+        _check(lib().p3m_get_stats(self._h, _p(d)))
+        return dict(zip(self.STAT_NAMES, (float(v) for v in d)))
+
+    @property
+    def fused_z(self):
+        return bool(self.stats()["fused_z"])
 
     @property
     def launches(self):

@@ -106,10 +106,13 @@ int upload_particles(p3m_ctx* c, const float* pos, const float* vel, const float
     P3M_LAUNCH_CHECK(c);
   }
   P3M_CUDA(cudaFreeAsync(stage, c->stream));
+  // the caller may reuse (pinned) pos / vel / mass as soon as this returns: wait for the copies
+  P3M_CUDA(cudaStreamSynchronize(c->stream));
   c->n = n;
   c->n_global = n;
   c->have_particles = true;
   c->sorted = false;
+  c->have_acc = true;  // all zero, in upload order
   {
     // equal masses?  (positive floats order like their bit patterns)
     float lo = n > 0 ? mass[0] : 0.f, hi = lo;
@@ -178,6 +181,7 @@ int upload_particles_ids(p3m_ctx* c, const float* pos, const float* vel, const f
     k_set_ids<T><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(stage, n, s.id);
     P3M_LAUNCH_CHECK(c);
     P3M_CUDA(cudaFreeAsync(stage, c->stream));
+    P3M_CUDA(cudaStreamSynchronize(c->stream));  // `ids` may be pinned memory the caller rewrites next
   }
   return 0;
 }
@@ -298,13 +302,13 @@ int bin_sort(p3m_ctx* c) {
   g.sbits = 0;
   if (g.p3m) {
     g.sbits = kSubBits;
-    if (const char* e = getenv("P3M_TUNE_SUBBITS")) g.sbits = atoi(e);  // tuning hook (measurements only)
+    if (c->tune.subbits >= 0) g.sbits = c->tune.subbits;  // tuning hook (measurements only)
     while (g.sbits > 0 && 3 * g.mbits + 3 * g.sbits + idbits > 62) --g.sbits;
   } else if (3 * g.mbits + 3 * g.tile_shift + idbits <= 62) {
     g.sbits = g.tile_shift;  // PM: sub key = mesh cell inside the tile (sort_kernels.cuh)
   }
   // PM-only contexts sort on a 32-bit (tile, mesh cell) key without the id (see k_keys)
-  const bool short_key = !g.p3m && 3 * g.mbits + 3 * g.sbits <= 32 && !getenv("P3M_TUNE_LONGKEY");
+  const bool short_key = !g.p3m && 3 * g.mbits + 3 * g.sbits <= 32 && !c->tune.long_key;
   const int lowbits = (short_key ? 0 : idbits) + 3 * g.sbits;
   const int keybits = lowbits + 3 * g.mbits;
   const long long ncells = 1LL << (3 * g.mbits);
@@ -332,6 +336,7 @@ int bin_sort(p3m_ctx* c) {
     std::swap(s.posm, s.posm_alt);
     std::swap(s.vel, s.vel_alt);
     std::swap(s.id, s.id_alt);
+    c->have_acc = false;  // acc / acc_sr were not permuted: stale until the next gather
     if (g.p3m) {
       const long long tiles = (n + kPPSub - 1) / kPPSub;
       k_tile_aabb<T><<<(unsigned)((tiles * 32 + 255) / 256), 256, 0, c->stream>>>(s.posm, n, s.aabb);

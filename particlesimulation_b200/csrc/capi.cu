@@ -1,6 +1,7 @@
 // capi.cu -- the extern "C" boundary declared in include/p3m_b200.h.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -16,6 +17,25 @@ int fail(int code, const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
+}
+
+void p3m_tune_load_impl(p3m_tune& t) {
+  auto flag = [](const char* name) {
+    const char* e = getenv(name);
+    return e && *e && !(e[0] == '0' && e[1] == 0);
+  };
+  if (const char* e = getenv("P3M_TUNE_SUBBITS")) t.subbits = atoi(e);
+  t.long_key = flag("P3M_TUNE_LONGKEY");
+  t.old_deposit = flag("P3M_TUNE_OLD_DEPOSIT");
+  t.static_cuts = flag("P3M_STATIC_CUTS");
+  t.count_cuts = flag("P3M_COUNT_CUTS");
+  if (const char* e = getenv("P3M_TUNE_PARTICLE_WEIGHT")) t.particle_weight = atof(e);
+  if (const char* e = getenv("P3M_TUNE_FFT_CHUNK_MB")) t.fft_chunk_bytes = atoll(e) << 20;
+  t.replicated_mesh = flag("P3M_REPLICATED_MESH");
+  t.cufft_z = flag("P3M_TUNE_CUFFT_Z");
+  t.full_sort = flag("P3M_TUNE_FULL_SORT");
+  t.scalar_pp = flag("P3M_TUNE_SCALAR_PP");
+  if (const char* e = getenv("P3M_TUNE_A2A_CHUNKS")) t.a2a_chunks = atoi(e);
 }
 
 void phase_begin(p3m_ctx* c, int ph) {
@@ -118,6 +138,8 @@ static int create_typed(p3m_ctx* c, const void* uid, int rank, int nranks) {
 
 using namespace p3m;
 
+void p3m_tune::load() { p3m::p3m_tune_load_impl(*this); }
+
 extern "C" {
 
 const char* p3m_last_error(void) { return g_err; }
@@ -167,6 +189,7 @@ static int create_common(const p3m_params* prm, const void* uid, int rank, int n
   p3m_ctx* c = new (std::nothrow) p3m_ctx();
   if (!c) return fail(P3M_EINVAL, "out of host memory");
   c->prm = *prm;
+  c->tune.load();
   c->device = dev;
   c->f64 = prm->precision == P3M_F64;
   c->timing = prm->timing != 0;
@@ -228,6 +251,7 @@ int p3m_balanced_cuts(const p3m_params* prm, int nranks, const float* pos, int64
     return fail(P3M_EINVAL, "p3m_balanced_cuts: bad argument");
   p3m_ctx c;
   c.prm = *prm;
+  c.tune.load();
   c.f64 = false;
   c.rank = 0, c.nranks = nranks;
   int r = setup_geometry<float>(&c);
@@ -248,6 +272,8 @@ int p3m_comm_unique_id(void* out) {
 }
 
 int p3m_create_dist(const p3m_params* prm, const void* uid, int rank, int nranks, p3m_ctx** out) {
+  if (nranks < 1 || nranks > P3M_MAX_RANKS || rank < 0 || rank >= nranks)
+    return fail(P3M_EINVAL, "p3m_create_dist: rank %d of %d (1..%d ranks supported)", rank, nranks, P3M_MAX_RANKS);
   if (!uid && nranks > 1) return fail(P3M_EINVAL, "p3m_create_dist: null unique id");
   return create_common(prm, uid, rank, nranks, out);
 }
@@ -256,6 +282,7 @@ int p3m_get_local(p3m_ctx* c, int32_t* ids, float* pos, float* vel, float* acc, 
   if (!c) return fail(P3M_EINVAL, "null context");
   P3M_CUDA(cudaSetDevice(c->device));
   if (!c->have_particles) return fail(P3M_ESTATE, "no particles set");
+  if (acc && c->n > 0 && !c->have_acc) return fail(P3M_ESTATE, "p3m_get_local: accelerations are stale (re-sorted since the last p3m_gather)");
   return P3M_DISPATCH(c, download_local, ids, pos, vel, acc, units);
 }
 
@@ -326,6 +353,7 @@ int p3m_set_particles(p3m_ctx* c, const float* pos, const float* vel, const floa
 int p3m_get_particles(p3m_ctx* c, float* pos, float* vel, float* acc, int units) {
   CHECK_CTX(c);
   if (!c->have_particles) return fail(P3M_ESTATE, "no particles set");
+  if (acc && c->n > 0 && !c->have_acc) return fail(P3M_ESTATE, "p3m_get_particles: accelerations are stale (re-sorted since the last p3m_gather)");
   return c->f64 ? download_particles<double, float>(c, pos, vel, acc, units)
                 : download_particles<float, float>(c, pos, vel, acc, units);
 }
@@ -333,6 +361,7 @@ int p3m_get_particles(p3m_ctx* c, float* pos, float* vel, float* acc, int units)
 int p3m_get_particles_f64(p3m_ctx* c, double* pos, double* vel, double* acc, int units) {
   CHECK_CTX(c);
   if (!c->have_particles) return fail(P3M_ESTATE, "no particles set");
+  if (acc && c->n > 0 && !c->have_acc) return fail(P3M_ESTATE, "p3m_get_particles_f64: accelerations are stale (re-sorted since the last p3m_gather)");
   return c->f64 ? download_particles<double, double>(c, pos, vel, acc, units)
                 : download_particles<float, double>(c, pos, vel, acc, units);
 }
@@ -400,6 +429,8 @@ int p3m_force(p3m_ctx* c) {
 
 int p3m_kick(p3m_ctx* c, float f) {
   CHECK_CTX(c);
+  if (c->have_particles && c->n > 0 && !c->have_acc)
+    return fail(P3M_ESTATE, "p3m_kick: accelerations are stale (particles were re-sorted since the last p3m_gather)");
   return P3M_DISPATCH(c, kick, (double)f);
 }
 int p3m_drift(p3m_ctx* c) {
@@ -435,6 +466,7 @@ int p3m_add_acceleration(p3m_ctx* c, const float* a, int units) {
   CHECK_CTX(c);
   if (!a) return fail(P3M_EINVAL, "null acceleration array");
   if (!c->have_particles) return fail(P3M_ESTATE, "no particles set");
+  if (c->n > 0 && !c->have_acc) return fail(P3M_ESTATE, "p3m_add_acceleration: accelerations are stale (re-sorted since the last p3m_gather)");
   return P3M_DISPATCH(c, add_acceleration, a, units);
 }
 
@@ -538,6 +570,7 @@ int p3m_chaining_neighbors(const int32_t M[3], int32_t cell, int32_t nb[14]) {
 int p3m_get_acc_parts(p3m_ctx* c, double* acc_pm, double* acc_sr) {
   CHECK_CTX(c);
   if (!c->have_particles) return fail(P3M_ESTATE, "no particles set");
+  if (c->n > 0 && !c->have_acc) return fail(P3M_ESTATE, "p3m_get_acc_parts: accelerations are stale (re-sorted since the last p3m_gather)");
   return P3M_DISPATCH(c, get_acc_parts, acc_pm, acc_sr);
 }
 
@@ -566,9 +599,10 @@ int p3m_get_phase_ms(p3m_ctx* c, float ms[P3M_NPHASE], int reset) {
 int p3m_get_pair_counts(p3m_ctx* c, uint64_t* checked, uint64_t* in_range) {
   CHECK_CTX(c);
   if (!c->prm.p3m) return fail(P3M_ESTATE, "PM-only context");
-  c->count_pairs = 1;
-  int r = P3M_DISPATCH(c, bin_sort);
-  if (r == 0) r = P3M_DISPATCH(c, short_range);
+  if (!c->have_particles || !c->sorted)
+    return fail(P3M_ESTATE, "p3m_get_pair_counts: call after p3m_short_range / p3m_force (particles must be sorted)");
+  c->count_pairs = 1;  // counting instantiation of the same kernels: reads only, no collective
+  int r = P3M_DISPATCH(c, short_range);
   c->count_pairs = 0;
   if (r != 0) return r;
   unsigned long long h[2];
@@ -577,6 +611,16 @@ int p3m_get_pair_counts(p3m_ctx* c, uint64_t* checked, uint64_t* in_range) {
   P3M_CUDA(cudaStreamSynchronize(c->stream));
   if (checked) *checked = h[0];
   if (in_range) *in_range = h[1];
+  return 0;
+}
+
+int p3m_get_stats(p3m_ctx* c, double out[P3M_NSTAT]) {
+  if (!c || !out) return fail(P3M_EINVAL, "null argument");
+  for (int i = 0; i < P3M_NSTAT; ++i) out[i] = 0;
+  out[0] = c->fused_z, out[1] = c->slab, out[2] = c->uniform_mass && c->prm.use_sr_table, out[3] = c->packed_pp;
+  out[4] = c->incr_sort, out[5] = c->stat_migrated, out[6] = (double)(c->f64 ? c->s64.n_ghost : c->s32.n_ghost);
+  out[7] = c->stat_a2a_bytes, out[8] = c->stat_den_bytes, out[9] = c->stat_pot_bytes, out[10] = c->stat_mig_bytes;
+  out[11] = c->stat_ghost_bytes, out[12] = c->stat_movers, out[13] = (double)c->full_sorts, out[14] = (double)c->incr_sorts;
   return 0;
 }
 

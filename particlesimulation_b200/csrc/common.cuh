@@ -72,7 +72,7 @@ struct Geom {
   // Binning-cell layers [cut[r], cut[r+1]) along z belong to rank r (the last rank also takes every
   // layer above cut[nranks]); lay0/lay1 = this rank's own range.
   int nranks, rank;
-  int cut[9];
+  int cut[P3M_MAX_RANKS + 1];
   int lay0, lay1;
   // planes held by the buffers the particle kernels address (single GPU: the whole mesh)
   long long den_off, den_len;  // density buffer = global flat indices [den_off, den_off + den_len)

@@ -69,8 +69,28 @@ struct State {
 
 }  // namespace p3m
 
+// Measurement switches, read from the environment ONCE when the context is created --
+// never on the per-step path.  Each selects an alternative, equally tested code path so that A/B numbers
+// come from one build; none is needed for normal use.
+struct p3m_tune {
+  int subbits = -1;             // P3M_TUNE_SUBBITS: sub-cell bits of the P3M sort key (-1 = default)
+  bool long_key = false;        // P3M_TUNE_LONGKEY: 64-bit sort key in PM-only contexts
+  bool old_deposit = false;     // P3M_TUNE_OLD_DEPOSIT: warp-private-tile deposit in PM-only contexts
+  bool static_cuts = false;     // P3M_STATIC_CUTS: geometric layer cuts
+  bool count_cuts = false;      // P3M_COUNT_CUTS: cuts by particle count also for P3M
+  double particle_weight = 300.0;  // P3M_TUNE_PARTICLE_WEIGHT: mesh-side work of a particle, in pair evaluations
+  long long fft_chunk_bytes = 1ll << 60;  // P3M_TUNE_FFT_CHUNK_MB: split the 2-D plane batches
+  bool replicated_mesh = false; // P3M_REPLICATED_MESH: full mesh + all-reduce instead of slabs
+  bool cufft_z = false;         // P3M_TUNE_CUFFT_Z: z leg through cuFFT + multiply kernel
+  bool full_sort = false;       // P3M_TUNE_FULL_SORT: radix-sort from scratch every step
+  bool scalar_pp = false;       // P3M_TUNE_SCALAR_PP: scalar-FFMA dense-cell kernel instead of the packed one
+  int a2a_chunks = 0;           // P3M_TUNE_A2A_CHUNKS: plane chunks of the overlapped slab FFT (0 = default)
+  void load();
+};
+
 struct p3m_ctx {
   p3m_params prm;
+  p3m_tune tune;
   int device = 0;
   cudaStream_t stream = nullptr;
   bool f64 = false;
@@ -78,6 +98,10 @@ struct p3m_ctx {
   long long cap = 0;      // allocated particle capacity
   bool have_particles = false, have_green = false, sorted = false, have_field = false;
   bool have_density = false, have_potential = false;
+  // acc[] / acc_sr[] belong to the CURRENT particle order.  A re-sort or a migration permutes positions,
+  // velocities and ids but not the accelerations, so it clears this flag; p3m_gather (or p3m_short_range on
+  // its own) sets it again.  p3m_kick, acceleration readbacks and diagnostics refuse to run without it.
+  bool have_acc = false;
   long long launches = 0;
   int steps_since_sort = 0;
   p3m::Geom<float> g32;
@@ -99,6 +123,11 @@ struct p3m_ctx {
   bool uniform_mass = false;
   double uniform_mass_code = 0;
   float mass_lo = 0, mass_hi = 0;
+  // p3m_get_stats: what the last force evaluation exchanged / how the last re-sort went
+  double stat_migrated = 0, stat_a2a_bytes = 0, stat_den_bytes = 0, stat_pot_bytes = 0, stat_mig_bytes = 0,
+         stat_ghost_bytes = 0, stat_movers = -1;
+  long long full_sorts = 0, incr_sorts = 0;
+  bool packed_pp = false, incr_sort = false;
   // multi-GPU (z-slabs of particles, NCCL): dist.cu
   void* nccl_comm = nullptr;  // ncclComm_t
   int rank = 0, nranks = 1;
@@ -107,7 +136,7 @@ struct p3m_ctx {
   bool slab = false;          // slab-decomposed mesh + distributed FFT (else: replicated mesh, all-reduce)
   // static plane ranges of every rank (identical on all ranks): density planes deposited by the
   // particle slab, unwrapped potential planes its gather needs
-  int den_z0[8] = {0}, den_nz[8] = {0}, pot_z0[8] = {0}, pot_nz[8] = {0};
+  int den_z0[P3M_MAX_RANKS] = {0}, den_nz[P3M_MAX_RANKS] = {0}, pot_z0[P3M_MAX_RANKS] = {0}, pot_nz[P3M_MAX_RANKS] = {0};
   int* dist_counts = nullptr;       // device: nranks + 1 segment starts, then nranks*nranks counts, then 4 ghost counts * nranks
   int* dist_counts_host = nullptr;  // pinned mirror
 };
@@ -182,7 +211,7 @@ template <typename T> int dist_allreduce_density(p3m_ctx* c);
 bool fused_z_supported(int nz);
 template <typename T> int fused_z_init(p3m_ctx* c);
 template <typename T> int fused_z_pass(p3m_ctx* c, void* spec, const T* green, long long ncols);
-int fft_chunk_planes(long long plane_bytes, int planes);
+int fft_chunk_planes(long long plane_bytes, int planes, long long budget);
 // dist_mesh.cu: slab-decomposed mesh
 template <typename T> int slab_setup(p3m_ctx* c);             // after dist_init: plane ranges, buffers, plans
 template <typename T> void slab_free(p3m_ctx* c);

@@ -445,7 +445,7 @@ int deposit(p3m_ctx* c) {
   c->launches++;
   int r = 0;
   const bool pm_cells = !g.p3m && g.tile_shift == kPmTileShift && g.sbits == g.tile_shift && g.is != P3M_NGP &&
-                        !getenv("P3M_TUNE_OLD_DEPOSIT");
+                        !c->tune.old_deposit;
   if (c->n > 0 && pm_cells) {
     r = g.is == P3M_TSC ? launch_deposit_pm<T, 3>(c) : launch_deposit_pm<T, 2>(c);
   } else if (c->n > 0) {

@@ -77,7 +77,7 @@ static void set_cuts(p3m_ctx* c) {
 // along z still lands on one rank.
 template <typename T>
 int dist_balance_cuts(p3m_ctx* c, const float* pos, long long n, int units) {
-  if (c->nranks <= 1 || n <= 0 || getenv("P3M_STATIC_CUTS")) return 0;
+  if (c->nranks <= 1 || n <= 0 || c->tune.static_cuts) return 0;
   Geom<T>& g = Sel<T>::g(c);
   const int P = c->nranks;
   set_cuts<T>(c);  // geometric cuts: defines the number of layers being cut
@@ -85,8 +85,7 @@ int dist_balance_cuts(p3m_ctx* c, const float* pos, long long n, int units) {
   // mesh-side work of one particle in units of one pair evaluation (sort + deposit + gather + integrate ~0.15-0.5
   // ns vs ~0.5-1 ps per pair on B200).  A caller that re-uploads all particles every step (bench.py's e2e loop)
   // is transfer-bound instead and wants a much larger value: P3M_TUNE_PARTICLE_WEIGHT overrides it.
-  double kPairsPerParticle = 300.0;
-  if (const char* e = getenv("P3M_TUNE_PARTICLE_WEIGHT")) kPairsPerParticle = atof(e);
+  const double kPairsPerParticle = c->tune.particle_weight;
   const double h[3] = {g.p3m ? (double)g.hcx : (double)(1 << g.tile_shift),
                        g.p3m ? (double)g.hcy : (double)(1 << g.tile_shift),
                        g.p3m ? (double)g.hcz : (double)(1 << g.tile_shift)};
@@ -94,7 +93,7 @@ int dist_balance_cuts(p3m_ctx* c, const float* pos, long long n, int units) {
   const double inv[3] = {u / h[0], u / h[1], u / h[2]};
   std::vector<double> weight((size_t)layers, 0.0);
   auto clampi = [](int v, int hi) { return v < 0 ? 0 : (v >= hi ? hi - 1 : v); };
-  if (!g.p3m || getenv("P3M_COUNT_CUTS")) {
+  if (!g.p3m || c->tune.count_cuts) {
     for (long long i = 0; i < n; ++i)
       weight[(size_t)clampi((int)std::floor((double)pos[3 * i + 2] * inv[2]), layers)] += 1.0;
   } else {
@@ -310,6 +309,11 @@ int dist_migrate(p3m_ctx* c, bool exchange) {
   }
   if (exchange) {
     long long off = keep;
+    long long sent = 0;
+    for (int p = 0; p < P; ++p)
+      if (p != me) sent += h[kCntMine + p];
+    c->stat_migrated = (double)sent;
+    c->stat_mig_bytes = (double)sent * (double)(2 * sizeof(V4<T>) + sizeof(int));
     P3M_NCCL(ncclGroupStart());
     for (int p = 0; p < P; ++p) {
       if (p == me) continue;
@@ -331,6 +335,7 @@ int dist_migrate(p3m_ctx* c, bool exchange) {
   }
   c->n = n_new;
   c->sorted = false;
+  c->have_acc = false;  // accelerations do not travel
   phase_end(c, PH_COMM);
   return 0;
 }
@@ -439,6 +444,7 @@ int dist_ghosts(p3m_ctx* c) {
   c->launches += 2;
   const long long ng = recv_lo + recv_hi;
   s.n_ghost = ng;
+  c->stat_ghost_bytes = (double)(send_lo + send_hi) * (double)(sizeof(V4<T>) + sizeof(int));
   // sort the ghosts by the same (cell, sub-cell, id) key and index them by cell
   if (ng > 0) {
     const unsigned blocks = (unsigned)((ng + 255) / 256);

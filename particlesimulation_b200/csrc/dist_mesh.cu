@@ -211,7 +211,7 @@ int slab_setup(p3m_ctx* c) {
   P3M_CUDA(cudaMemsetAsync(s.pot_part, 0, sizeof(T) * plane * (size_t)c->pot_nz[me], c->stream));
   const bool dbl = sizeof(T) == 8;
   int n2[2] = {g.ny, g.nx};
-  s.fft_chunk = fft_chunk_planes((long long)nxh * g.ny * sizeof(cplx), nzl);
+  s.fft_chunk = fft_chunk_planes((long long)nxh * g.ny * sizeof(cplx), nzl, c->tune.fft_chunk_bytes);
   P3M_FFT(cufftPlanMany(&s.plan_fwd, 2, n2, nullptr, 1, 0, nullptr, 1, 0, dbl ? CUFFT_D2Z : CUFFT_R2C, s.fft_chunk));
   P3M_FFT(cufftPlanMany(&s.plan_inv, 2, n2, nullptr, 1, 0, nullptr, 1, 0, dbl ? CUFFT_Z2D : CUFFT_C2R, s.fft_chunk));
   s.plans = true;
@@ -243,12 +243,14 @@ int slab_reduce_density(p3m_ctx* c) {
     return hi > lo;
   };
   P3M_CUDA(cudaMemsetAsync(s.density, 0, sizeof(T) * plane * nzl, c->stream));
-  size_t stage_off[8] = {0};
+  size_t stage_off[P3M_MAX_RANKS] = {0};
   size_t off = 0;
+  double sent = 0;
   P3M_NCCL(ncclGroupStart());
   for (int p = 0; p < P; ++p) {
     if (p == me) continue;
     int lo, hi;
+    if (overlap(me, p, lo, hi)) sent += (double)(hi - lo) * (double)plane * sizeof(T);
     if (overlap(me, p, lo, hi))
       P3M_NCCL(ncclSend(s.dens_part + (size_t)(lo - c->den_z0[me]) * plane, (size_t)(hi - lo) * plane, nccl_real<T>(), p,
                         comm, c->stream));
@@ -260,6 +262,7 @@ int slab_reduce_density(p3m_ctx* c) {
   }
   P3M_NCCL(ncclGroupEnd());
   c->launches++;
+  c->stat_den_bytes = sent;
   // sum in rank order: bit-reproducible
   for (int p = 0; p < P; ++p) {
     int lo, hi;
@@ -288,10 +291,12 @@ int slab_spread_potential(p3m_ctx* c) {
     hi = std::min((own + 1) * nzl + k * g.nz, c->pot_z0[dst] + c->pot_nz[dst]);
     return hi > lo;
   };
+  double sent = 0;
   P3M_NCCL(ncclGroupStart());
   for (int p = 0; p < P; ++p)
     for (int k = -1; k <= 1; ++k) {
       int lo, hi;
+      if (p != me && overlap(me, k, p, lo, hi)) sent += (double)(hi - lo) * (double)plane * sizeof(T);
       if (p != me && overlap(me, k, p, lo, hi))
         P3M_NCCL(ncclSend(s.potential + (size_t)(lo - k * g.nz - me * nzl) * plane, (size_t)(hi - lo) * plane,
                           nccl_real<T>(), p, comm, c->stream));
@@ -301,6 +306,7 @@ int slab_spread_potential(p3m_ctx* c) {
     }
   P3M_NCCL(ncclGroupEnd());
   c->launches++;
+  c->stat_pot_bytes = sent;
   for (int k = -1; k <= 1; ++k) {
     int lo, hi;
     if (overlap(me, k, me, lo, hi))
@@ -328,6 +334,7 @@ static int all_to_all(p3m_ctx* c, typename State<T>::cplx* send, typename State<
   P3M_CUDA(cudaMemcpyAsync(recv + (size_t)me * chunk, send + (size_t)me * chunk, chunk * sizeof(cplx),
                            cudaMemcpyDeviceToDevice, c->stream));
   c->launches += 2;
+  c->stat_a2a_bytes += (double)(P - 1) * (double)chunk * sizeof(cplx);
   return 0;
 }
 
@@ -342,6 +349,7 @@ int slab_poisson(p3m_ctx* c) {
   const size_t chunk = (size_t)nxh * nyl * nzl;
   const int grid = grid_for(spec, c->num_sms);
   const size_t plane = (size_t)g.nx * g.ny, splane = (size_t)nxh * g.ny;
+  c->stat_a2a_bytes = 0;
   phase_begin(c, PH_FFT_FWD);
   for (int z = 0; z < nzl; z += s.fft_chunk) {
     P3M_FFT(exec_r2c(s.plan_fwd, s.density + plane * z, s.spectrum + splane * z));

@@ -419,6 +419,7 @@ int gather(p3m_ctx* c) {
     else r = launch_gather<T, 1, 2>(c);
   }
   phase_end(c, PH_GATHER);
+  if (r == 0) c->have_acc = true;
   return r;
 }
 

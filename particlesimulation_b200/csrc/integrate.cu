@@ -174,6 +174,8 @@ k_diag_mesh(const T* __restrict__ rho, const T* __restrict__ phi, long long firs
 template <typename T>
 int diagnostics(p3m_ctx* c, double* out) {
   if (!c->have_particles) return fail(P3M_ESTATE, "p3m_diagnostics: no particles set");
+  if (c->n > 0 && !c->have_acc)
+    return fail(P3M_ESTATE, "p3m_diagnostics: accelerations are stale (re-sorted since the last p3m_gather)");
   State<T>& s = Sel<T>::st(c);
   const Geom<T>& g = Sel<T>::g(c);
   P3M_CUDA(cudaMemsetAsync(s.diag, 0, sizeof(double) * 16, c->stream));

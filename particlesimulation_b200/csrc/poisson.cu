@@ -261,9 +261,7 @@ static cufftResult exec_inv(cufftHandle p, cufftDoubleComplex* in, double* out) 
 // planes per batched 2-D transform.  Measured on B200 (512^3): splitting the batch so that the intermediate of
 // cuFFT's two passes would stay in L2 is SLOWER than one batch over all planes (2.39 vs 1.73 ms per solve),
 // so the default is one batch; P3M_TUNE_FFT_CHUNK_MB re-enables the split for measurements.
-int fft_chunk_planes(long long plane_bytes, int planes) {
-  long long budget = 1ll << 60;
-  if (const char* e = getenv("P3M_TUNE_FFT_CHUNK_MB")) budget = atoll(e) << 20;
+int fft_chunk_planes(long long plane_bytes, int planes, long long budget) {
   int cp = 1;
   while (cp * 2 <= planes && (long long)(cp * 2) * plane_bytes <= budget && planes % (cp * 2) == 0) cp *= 2;
   return cp;
@@ -276,8 +274,8 @@ int alloc_meshes(p3m_ctx* c) {
   const p3m_params& p = c->prm;
   const long long hc = half_count(p);
   // several ranks: slab-decomposed mesh whenever the planes and the ky rows divide evenly
-  c->slab = c->nranks > 1 && p.nz % c->nranks == 0 && p.ny % c->nranks == 0 && !getenv("P3M_REPLICATED_MESH");
-  c->fused_z = fused_z_supported(p.nz) && !getenv("P3M_TUNE_CUFFT_Z");
+  c->slab = c->nranks > 1 && p.nz % c->nranks == 0 && p.ny % c->nranks == 0 && !c->tune.replicated_mesh;
+  c->fused_z = fused_z_supported(p.nz) && !c->tune.cufft_z;
   if (c->fused_z) P3M_TRY(fused_z_init<T>(c));
   if (c->slab) {
     P3M_TRY(slab_setup<T>(c));
@@ -293,7 +291,7 @@ int alloc_meshes(p3m_ctx* c) {
     const bool dbl = sizeof(T) == 8;
     if (c->fused_z) {
       // batched 2-D transforms of the planes; the z leg is k_poisson_z
-      s.fft_chunk = fft_chunk_planes((long long)(p.nx / 2 + 1) * p.ny * sizeof(typename State<T>::cplx), p.nz);
+      s.fft_chunk = fft_chunk_planes((long long)(p.nx / 2 + 1) * p.ny * sizeof(typename State<T>::cplx), p.nz, c->tune.fft_chunk_bytes);
       int n2[2] = {p.ny, p.nx};
       P3M_FFT(cufftPlanMany(&s.plan_fwd, 2, n2, nullptr, 1, 0, nullptr, 1, 0, dbl ? CUFFT_D2Z : CUFFT_R2C, s.fft_chunk));
       P3M_FFT(cufftPlanMany(&s.plan_inv, 2, n2, nullptr, 1, 0, nullptr, 1, 0, dbl ? CUFFT_Z2D : CUFFT_C2R, s.fft_chunk));

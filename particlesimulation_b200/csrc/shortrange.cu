@@ -343,12 +343,12 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
             }
           }
         }
-    if (v0) {
+    if (!COUNT && v0) {  // the counting instantiation is read-only: p3m_get_pair_counts has no side effects
       acc_sr[i0] = V4<T>{a0x, a0y, a0z, 0};
       V4<T> a = acc[i0];
       acc[i0] = V4<T>{a.x + a0x, a.y + a0y, a.z + a0z, 0};  // correctAccelerations :55
     }
-    if (v1) {
+    if (!COUNT && v1) {
       acc_sr[i1] = V4<T>{a1x, a1y, a1z, 0};
       V4<T> a = acc[i1];
       acc[i1] = V4<T>{a.x + a1x, a.y + a1y, a.z + a1z, 0};
@@ -404,9 +404,11 @@ k_pp_sparse(const V4<T>* __restrict__ posm, long long n, const int* __restrict__
                                               sp, tref, ax, ay, az, n_in);
         }
       }
-  acc_sr[i] = V4<T>{ax, ay, az, 0};
-  const V4<T> a = acc[i];
-  acc[i] = V4<T>{a.x + ax, a.y + ay, a.z + az, 0};
+  if (!COUNT) {
+    acc_sr[i] = V4<T>{ax, ay, az, 0};
+    const V4<T> a = acc[i];
+    acc[i] = V4<T>{a.x + ax, a.y + ay, a.z + az, 0};
+  }
   if (COUNT) {
     atomicAdd(&pair_counts[0], checked);
     atomicAdd(&pair_counts[1], (unsigned long long)n_in);
@@ -454,7 +456,7 @@ int sr_table_upload(p3m_ctx* c) {
   const p3m_params& p = c->prm;
   // code-unit lengths, source/p3mMethod.cpp:35-37,42-44
   const T re = (T)p.cutoff_radius / (T)p.H;
-  sp.a = (T)p.particle_diameter / (T)p.H;
+  sp.a = (T)(p.sr_particle_diameter > 0 ? p.sr_particle_diameter : p.particle_diameter) / (T)p.H;
   const T eps = (T)p.softening / (T)p.H;
   const T delta2 = re * re / (kSRTable - 1);
   sp.re2 = re * re;
@@ -530,6 +532,12 @@ int short_range(p3m_ctx* c) {
   if (!c->prm.p3m) return 0;
   if (!c->have_particles || !c->sorted) return fail(P3M_ESTATE, "p3m_short_range: particles not sorted");
   if (c->n == 0) return 0;
+  if (!c->have_acc && !c->count_pairs) {
+    // no mesh part for the current particle order (p3m_gather was not run since the last sort): the
+    // short-range part is then the whole acceleration
+    P3M_CUDA(cudaMemsetAsync(Sel<T>::st(c).acc, 0, sizeof(V4<T>) * (size_t)c->n, c->stream));
+    c->have_acc = true;
+  }
   phase_begin(c, PH_SHORT_RANGE);
   int r;
   const bool table = c->prm.use_sr_table != 0, count = c->count_pairs != 0;

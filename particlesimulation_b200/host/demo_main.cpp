@@ -104,6 +104,8 @@ int main(int argc, char** argv) {
       PMMethod pm(state, masses, effectiveBoxSize, externalField, externalPotential, H, DT, G,
                   InterpolationScheme::TSC, FiniteDiffScheme::TWO_POINT, GreensFunction::S1_OPTIMAL, particleDiam,
                   gridPoints);
+      // a non-empty callable is evaluated on the host every step; declare the zero field instead
+      if (!std::getenv("DEMO_HOST_CALLBACK")) pm.setExternalFieldDescriptor(ExternalFieldDesc::none());
       float re = 0.7f * particleDiam;
       float softeningLength = 0.5f;
       P3MMethod p3m(pm, effectiveBoxSize, re, particleDiam, H, softeningLength, CloudShape::S1);

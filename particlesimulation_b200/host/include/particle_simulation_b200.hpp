@@ -1,14 +1,25 @@
 // particle_simulation_b200.hpp -- the reference's C++ API surface for the P3M / PM path, re-hosted on
 // the B200 library.  A caller of AleksyBalazinski/ParticleSimulation (its source/demos.cpp, or any
 // code written against include/pmMethod.h, include/p3mMethod.h, include/grid.h, include/FFTAdapter.h,
-// include/greensFunctions.h, include/chainingMesh.h, include/leapfrog.h, include/abstractStepper.h)
-// compiles against these declarations unchanged: same class names, constructor argument order,
-// member names and error behaviour.  The bodies (host/src/*.cpp) are thin callers of the C ABI in
-// include/p3m_b200.h; particles live on the GPU and the host std::vector<Particle> is only
-// materialised when the caller asks for it.
+// include/greensFunctions.h, include/chainingMesh.h, include/leapfrog.h, include/simInfo.h,
+// include/unitConversions.h) compiles against these declarations unchanged: same class names,
+// constructor argument order, member names and error behaviour.  The bodies (host/src/*.cpp) are thin
+// callers of the C ABI in include/p3m_b200.h; particles live on the GPU and the host
+// std::vector<Particle> is only materialised when the caller asks for it.
 //
-// Forwarding headers with the reference's file names (pmMethod.h, p3mMethod.h, ...) sit next to this
-// file so `#include "pmMethod.h"` keeps working.
+// Two ways to build against it:
+//  * INSIDE the reference checkout ("reference-tree mode"):  -I <this dir> -I <reference>/include.
+//    The headers this directory provides (pmMethod.h, p3mMethod.h, PMMethodGPU.h, grid.h, greensFunctions.h,
+//    chainingMesh.h, leapfrog.h, simInfo.h, unitConversions.h, cuFFTAdapter.h) shadow the reference's; the
+//    plain data types the rest of the reference tree shares -- Vec3, Particle, the pmConfig enums,
+//    StateRecorder, FFTAdapter<T>, AbstractStepper<T>, the external-field functions -- are NOT redefined
+//    here: the reference's own vec3.h / particle.h / pmConfig.h / stateRecorder.h / FFTAdapter.h /
+//    abstractStepper.h / externalFields.h are included, so samplers, Barnes-Hut, the direct-sum method and
+//    the demos keep compiling in the same translation unit, and host/src/*.cpp are compiled in place of
+//    pmMethod.cpp, p3mMethod.cpp, grid.cpp, greensFunctions.cpp, chainingMesh.cpp, leapfrog.cpp,
+//    simInfo.cpp and unitConversions.cpp.
+//  * WITHOUT the reference ("standalone mode"):  -I <this dir> -I <this dir>/standalone.  The same plain
+//    types are defined below and implemented in host/src/support.cpp (libparticlesim_host.so).
 #pragma once
 
 #include <array>
@@ -24,6 +35,25 @@
 
 struct p3m_ctx;  // include/p3m_b200.h
 
+#if !defined(P3M_B200_STANDALONE) && __has_include("p3m_b200_standalone.h")
+#include "p3m_b200_standalone.h"
+#endif
+#if !defined(P3M_B200_STANDALONE) && __has_include("vec3.h") && __has_include("particle.h") && \
+    __has_include("pmConfig.h") && __has_include("stateRecorder.h") && __has_include("FFTAdapter.h") && \
+    __has_include("abstractStepper.h") && __has_include("externalFields.h")
+#define P3M_B200_REFERENCE_TREE 1
+#include "FFTAdapter.h"
+#include "abstractStepper.h"
+#include "externalFields.h"
+#include "particle.h"
+#include "pmConfig.h"
+#include "stateRecorder.h"
+#include "vec3.h"
+#else
+#define P3M_B200_REFERENCE_TREE 0
+#endif
+
+#if !P3M_B200_REFERENCE_TREE
 // ---- include/vec3.h ---------------------------------------------------------------------------------
 struct Vec3 {
   float x{};
@@ -68,6 +98,9 @@ struct Particle {
 enum class InterpolationScheme { NGP, CIC, TSC };
 enum class FiniteDiffScheme { TWO_POINT, FOUR_POINT };
 enum class GreensFunction { DISCRETE_LAPLACIAN, S1_OPTIMAL, S2_OPTIMAL, POOR_MAN };
+#endif  // !P3M_B200_REFERENCE_TREE
+
+// ---- include/greensFunctions.h ---------------------------------------------------------------------------
 enum class CloudShape { S1, S2 };
 
 // Single-mode evaluations with the reference's signatures (host, double inside, float out); the run
@@ -77,6 +110,7 @@ std::complex<float> GreenOptimal(InterpolationScheme is, int kx, int ky, int kz,
 std::complex<float> GreenDiscreteLaplacian(int kx, int ky, int kz, std::tuple<int, int, int> dims);
 std::complex<float> GreenPoorMan(int kx, int ky, int kz, std::tuple<int, int, int> dims);
 
+#if !P3M_B200_REFERENCE_TREE
 // ---- include/FFTAdapter.h ------------------------------------------------------------------------------
 template <typename T>
 class FFTAdapter {
@@ -85,6 +119,8 @@ class FFTAdapter {
   virtual std::vector<std::complex<T>>& fft(std::vector<std::complex<T>>& in, std::vector<std::complex<T>>& out) = 0;
   virtual std::vector<std::complex<T>>& ifft(std::vector<std::complex<T>>& in, std::vector<std::complex<T>>& out) = 0;
 };
+
+#endif  // !P3M_B200_REFERENCE_TREE
 
 // The GPU backend as a proper FFTAdapter<float> (the reference's CuFFTAdapter does not derive from
 // the interface).  dims = {Nz, Ny, Nx} as every reference adapter takes them
@@ -141,6 +177,7 @@ class Grid {
   FFTAdapter<float>& fftAdapter;
 };
 
+#if !P3M_B200_REFERENCE_TREE
 // ---- include/stateRecorder.h (file formats of SURVEY section 8f row N2) ------------------------------
 class StateRecorder {
  public:
@@ -169,32 +206,48 @@ class StateRecorder {
   int particlesCnt, framesCnt;
 };
 
-// ---- include/simInfo.h (the members the run loops use) ---------------------------------------------------
+#endif  // !P3M_B200_REFERENCE_TREE
+
+// ---- include/simInfo.h -------------------------------------------------------------------------------
 class SimInfo {
  public:
+  // state-vector overloads (include/simInfo.h:11-24; used by the reference's direct-sum method)
+  static float potentialEnergy(std::vector<Vec3>::iterator posBegin, std::vector<Vec3>::iterator posEnd,
+                               const std::vector<float>& masses, float G);
+  static float kineticEnergy(std::vector<Vec3>::iterator vBegin, std::vector<Vec3>::iterator vEnd,
+                             const std::vector<float>& masses, float G);
+  static Vec3 totalMomentum(std::vector<Vec3>::iterator vBegin, std::vector<Vec3>::iterator vEnd,
+                            const std::vector<float>& masses);
+  // mesh overloads (include/simInfo.h:26-36): from a host Grid, or from the density / potential vectors of
+  // the CUDA-build PMMethodGPU (getGridDensity / getGridPotential), as source/p3mMethod.cpp:121-122 calls it
+  static float potentialEnergy(const Grid& grid, const std::vector<Particle>& particles,
+                               std::function<float(Vec3)> externalPotential, float H, float DT, float G);
+  static float potentialEnergy(const std::vector<std::complex<float>>& gridDensity,
+                               const std::vector<std::complex<float>>& gridPotential,
+                               const std::vector<Particle>& particles, std::function<float(Vec3)> externalPotential,
+                               float H, float DT, float G);
   static float kineticEnergy(const std::vector<Particle>& particles);
   static Vec3 totalMomentum(const std::vector<Particle>& particles);
   static Vec3 totalAngularMomentum(const std::vector<Particle>& particles);
-  static float potentialEnergy(const Grid& grid, const std::vector<Particle>& particles,
-                               std::function<float(Vec3)> externalPotential, float H, float DT, float G);
-  void setInitialMomentum(const std::vector<Particle>& particles) { expectedMomentum = totalMomentum(particles); }
-  void setInitialMomentum(Vec3 p) { expectedMomentum = p; }
-  Vec3 updateExpectedMomentum(Vec3 externalForce, float DT) {
-    expectedMomentum += DT * externalForce;
-    return expectedMomentum;
-  }
+  void setInitialMomentum(const std::vector<Particle>& particles);
+  Vec3 updateExpectedMomentum(Vec3 externalForce, float DT);
 
  private:
   Vec3 expectedMomentum;
 };
 
+#if !P3M_B200_REFERENCE_TREE
 // ---- source/externalFields.cpp ---------------------------------------------------------------------------
 Vec3 sphRadDecrField(Vec3 pos, Vec3 center, float R, float M, float G);
 float sphRadDecrFieldPotential(Vec3 pos, Vec3 center, float R, float M, float G);
 
-// An external field the device can evaluate itself.  std::function fields cannot cross to the GPU;
-// PMMethod recognises the zero field by probing, otherwise pass one of these (or fall back to the
-// per-step host callback, which is correct but slow).
+#endif  // !P3M_B200_REFERENCE_TREE
+
+// An external field the device can evaluate itself.  std::function fields cannot cross to the GPU: an EMPTY
+// std::function means "no field"; any other callable is evaluated on the host once per particle per step
+// (download positions, call, upload accelerations -- correct for every field, but slow).  Installing a
+// descriptor (PMMethod::setExternalFieldDescriptor) moves the evaluation into the gather kernel; the
+// descriptor then REPLACES the callable, so pass the matching one (none() for an identically zero lambda).
 struct ExternalFieldDesc {
   enum Kind { NONE = 0, SPH_RAD_DECR = 1 } kind = NONE;
   Vec3 center{};
@@ -229,7 +282,7 @@ class PMMethod {
   float getH() const { return H; }
   float getDT() const { return DT; }
   float getG() const { return G; }
-  const Grid& getGrid();  // back-fills density and potential from the device
+  const Grid& getGrid() const;  // back-fills density and potential from the device (include/pmMethod.h:37)
   std::function<float(Vec3)> getExternalPotential() const { return externalPotential; }
   void pmMethodStep();
   bool escapedComputationalBox();
@@ -237,8 +290,9 @@ class PMMethod {
   void initGreensFunction();
 
   // PMMethodGPU extras (include_gpu/PMMethodGPU.h:38-54)
-  const std::vector<std::complex<float>>& getGridDensity();
-  const std::vector<std::complex<float>>& getGridPotential();
+  // the getters return the vectors as of the last copyGrid*ToHost(), like the reference's
+  const std::vector<std::complex<float>>& getGridDensity() const;
+  const std::vector<std::complex<float>>& getGridPotential() const;
   void copyParticlesDeviceToHost();
   void copyParticlesHostToDevice();
   void copyGridPotentialToHost();
@@ -307,12 +361,15 @@ void setIntegerStepVelocities(std::vector<Particle>& particles, float dt = 1.0f)
 void updateVelocities(std::vector<Particle>& particles, float dt = 1.0f);
 void updatePositions(std::vector<Particle>& particles, float dt = 1.0f);
 
+#if !P3M_B200_REFERENCE_TREE
 template <typename T>
 class AbstractStepper {
  public:
   virtual ~AbstractStepper() {}
   virtual void doStep(std::vector<T>& x, float dt) = 0;
 };
+
+#endif  // !P3M_B200_REFERENCE_TREE
 
 // Kick-drift-kick leapfrog as an AbstractStepper over Particle (the reference only implements the
 // interface for RK4; its leapfrog is the four free functions above).
@@ -326,19 +383,28 @@ class LeapfrogStepper : public AbstractStepper<Particle> {
   std::function<void(std::vector<Particle>&)> force;
 };
 
+// include/unitConversions.h:8-71 (all of it: the reference's stateRecorder.cpp, ppMethod.cpp and barnesHut.cpp
+// include this header too)
 inline Vec3 positionToCodeUntits(const Vec3& pos, float H) { return pos / H; }
 inline Vec3 positionToOriginalUnits(const Vec3& pos, float H) { return H * pos; }
 inline Vec3 velocityToCodeUntits(const Vec3& v, float H, float DT) { return DT * v / H; }
 inline Vec3 velocityToOriginalUnits(const Vec3& v, float H, float DT) { return H * v / DT; }
 inline Vec3 accelerationToCodeUnits(const Vec3& a, float H, float DT) { return DT * DT * a / H; }
 inline Vec3 accelerationToOriginalUnits(const Vec3& a, float H, float DT) { return H * a / (DT * DT); }
-float densityToCodeUnits(float density, float DT, float G);
-float densityToOriginalUnits(float density, float DT, float G);
+inline constexpr float kP3mPiF = 3.14159265358979323846f;  // == std::numbers::pi_v<float>
+inline float densityToCodeUnits(float density, float DT, float G) { return DT * DT * 4 * kP3mPiF * G * density; }
+inline float densityToOriginalUnits(float density, float DT, float G) { return density / (DT * DT * 4 * kP3mPiF * G); }
 inline float potentialToOriginalUnits(float potential, float H, float DT) { return potential * H * H / (DT * DT); }
-float massToCodeUnits(float m, float H, float DT, float G);
-float massToOriginalUnits(float m, float H, float DT, float G);
+inline float massToCodeUnits(float m, float H, float DT, float G) { return DT * DT * 4 * kP3mPiF * G / (H * H * H) * m; }
+inline float massToOriginalUnits(float m, float H, float DT, float G) { return (H * H * H) / (DT * DT * 4 * kP3mPiF * G) * m; }
 inline float lengthToCodeUnits(float x, float H) { return x / H; }
+void stateToCodeUnits(std::vector<Vec3>& state, float H, float DT);
+void stateToOriginalUnits(std::vector<Vec3>& state, float H, float DT);
 void stateToCodeUnits(std::vector<Particle>& particles, float H, float DT);
 void stateToOriginalUnits(std::vector<Particle>& particles, float H, float DT);
+void velocitiesToCodeUnits(std::vector<Vec3>& velocities, float H, float DT);
+void velocitiesToOriginalUnits(std::vector<Vec3>& velocities, float H, float DT);
+void integerStepVelocitiesToOriginalUnits(std::vector<Particle>& particles, float H, float DT);
+void integerStepVelocitiesToCodeUnits(std::vector<Particle>& particles, float H, float DT);
 void massToCodeUnits(std::vector<Particle>& particles, float H, float DT, float G);
 void massToOriginalUnits(std::vector<Particle>& particles, float H, float DT, float G);

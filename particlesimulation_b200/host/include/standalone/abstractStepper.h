@@ -1,3 +1,3 @@
 // forwarding header: the reference API of include/abstractStepper.h lives in particle_simulation_b200.hpp
 #pragma once
-#include "particle_simulation_b200.hpp"
+#include "../particle_simulation_b200.hpp"

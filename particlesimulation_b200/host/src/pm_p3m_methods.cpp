@@ -36,8 +36,9 @@ struct PMMethod::Impl {
   Grid* grid = nullptr;
   std::unique_ptr<CuFFTAdapter> ownedFft;
   std::unique_ptr<Grid> ownedGrid;
-  bool extIsZero = true;     // std::function field probed to be identically zero
-  bool extOnDevice = false;  // ExternalFieldDesc installed
+  bool extIsZero = true;     // no field at all: empty std::function, or ExternalFieldDesc::none() installed
+  bool extOnDevice = false;  // an ExternalFieldDesc was installed: the device evaluates it, the callable is unused
+  std::vector<std::complex<float>> gridDensity, gridPotential;  // PMMethodGPU::getGridDensity / getGridPotential
   std::vector<float> scratch, scratch2;
 
   ~Impl() {
@@ -63,7 +64,9 @@ struct PMMethod::Impl {
       const Particle& p = particles[i];
       pos[3 * i] = p.position.x, pos[3 * i + 1] = p.position.y, pos[3 * i + 2] = p.position.z;
       vel[3 * i] = p.velocity.x, vel[3 * i + 1] = p.velocity.y, vel[3 * i + 2] = p.velocity.z;
-      mass[i] = p.mass;
+      // masses always come from the constructor's vector (the host mirror's p.mass follows the units of the
+      // mirror); converted with the reference's own fp32 expression (include/unitConversions.h:42-44)
+      mass[i] = hostUnitsCode ? massToCodeUnits(massOriginal[i], prm.H, prm.DT, prm.G) : massOriginal[i];
     }
     check(p3m_set_particles(ctx, pos, vel, mass, (int64_t)n, hostUnitsCode ? P3M_UNITS_CODE : P3M_UNITS_ORIGINAL),
           "p3m_set_particles");
@@ -83,11 +86,14 @@ struct PMMethod::Impl {
       p.position = Vec3{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
       p.velocity = Vec3{vel[3 * i], vel[3 * i + 1], vel[3 * i + 2]};
       p.acceleration = Vec3{acc[3 * i], acc[3 * i + 1], acc[3 * i + 2]};  // always code units in the reference
+      p.integerStepVelocity = p.velocity + 0.5f * p.acceleration;         // source/leapfrog.cpp:10-14, code units
+      p.mass = massToCodeUnits(massOriginal[i], H, DT, prm.G);
       if (!hostUnitsCode) {
         p.position = positionToOriginalUnits(p.position, H);
         p.velocity = velocityToOriginalUnits(p.velocity, H, DT);
+        p.integerStepVelocity = velocityToOriginalUnits(p.integerStepVelocity, H, DT);
+        p.mass = massOriginal[i];
       }
-      p.integerStepVelocity = p.velocity + 0.5f * p.acceleration;
     }
     deviceIsNewer = false;
   }
@@ -117,16 +123,6 @@ static void fillParams(p3m_params& prm, std::tuple<int, int, int> gridPoints,
   prm.p3m = 0;
 }
 
-static bool probeZeroField(const std::function<Vec3(Vec3)>& f, const std::vector<Vec3>& state, size_t n) {
-  if (!f) return true;
-  const size_t step = n > 16 ? n / 16 : 1;
-  for (size_t i = 0; i < n; i += step) {
-    Vec3 g = f(state[i]);
-    if (g.x != 0 || g.y != 0 || g.z != 0) return false;
-  }
-  Vec3 g = f(Vec3{1.25f, 2.5f, 3.75f});
-  return g.x == 0 && g.y == 0 && g.z == 0;
-}
 
 PMMethod::PMMethod(const std::vector<Vec3>& state, const std::vector<float>& masses,
                    const std::tuple<float, float, float> effectiveBoxSize,
@@ -141,7 +137,8 @@ PMMethod::PMMethod(const std::vector<Vec3>& state, const std::vector<float>& mas
   impl->particles.reserve(n);
   for (size_t i = 0; i < n; ++i) impl->particles.emplace_back(state[i], state[n + i], masses[i]);
   impl->massOriginal = masses;
-  impl->extIsZero = probeZeroField(externalField, state, n);
+  // a callable cannot be proven zero by sampling it: only an EMPTY std::function means "no field"
+  impl->extIsZero = !externalField;
 }
 
 PMMethod::PMMethod(const std::vector<Vec3>& state, const std::vector<float>& masses,
@@ -161,7 +158,7 @@ PMMethod::PMMethod(const std::vector<Vec3>& state, const std::vector<float>& mas
   impl->particles.reserve(n);
   for (size_t i = 0; i < n; ++i) impl->particles.emplace_back(state[i], state[n + i], masses[i]);
   impl->massOriginal = masses;
-  impl->extIsZero = probeZeroField(externalField, state, n);
+  impl->extIsZero = !externalField;
 }
 
 PMMethod::~PMMethod() = default;
@@ -170,7 +167,8 @@ void PMMethod::setExternalFieldDescriptor(const ExternalFieldDesc& d) {
   impl->prm.ext_kind = (int)d.kind;
   impl->prm.ext_center[0] = d.center.x, impl->prm.ext_center[1] = d.center.y, impl->prm.ext_center[2] = d.center.z;
   impl->prm.ext_R = d.R, impl->prm.ext_M = d.M;
-  impl->extOnDevice = d.kind != ExternalFieldDesc::NONE;
+  impl->extOnDevice = true;  // the descriptor replaces the callable (none(): explicitly no field)
+  impl->extIsZero = d.kind == ExternalFieldDesc::NONE;
   if (impl->ctx) {
     impl->download();
     impl->dropCtx();
@@ -250,7 +248,8 @@ void PMMethod::copyGridDensityToHost() {
   impl->scratch2.resize(M);
   check(p3m_get_density(impl->ctx, impl->scratch2.data()), "p3m_get_density");
   auto& d = impl->grid->densityStorage();
-  for (int i = 0; i < M; ++i) d[i] = std::complex<float>(impl->scratch2[i], 0.0f);
+  impl->gridDensity.resize(M);
+  for (int i = 0; i < M; ++i) impl->gridDensity[i] = d[i] = std::complex<float>(impl->scratch2[i], 0.0f);
 }
 
 void PMMethod::copyGridPotentialToHost() {
@@ -259,24 +258,23 @@ void PMMethod::copyGridPotentialToHost() {
   impl->scratch2.resize(M);
   check(p3m_get_potential(impl->ctx, impl->scratch2.data()), "p3m_get_potential");
   auto& d = impl->grid->potentialStorage();
-  for (int i = 0; i < M; ++i) d[i] = std::complex<float>(impl->scratch2[i], 0.0f);
+  impl->gridPotential.resize(M);
+  for (int i = 0; i < M; ++i) impl->gridPotential[i] = d[i] = std::complex<float>(impl->scratch2[i], 0.0f);
 }
 
-const Grid& PMMethod::getGrid() {
+// include/pmMethod.h:37 is const; the meshes live on the device, so the host Grid is refreshed first
+// (impl is a pointer: the refresh does not touch this object's own members)
+const Grid& PMMethod::getGrid() const {
   if (impl->ctx) {
-    copyGridDensityToHost();
-    copyGridPotentialToHost();
+    PMMethod* self = const_cast<PMMethod*>(this);
+    self->copyGridDensityToHost();
+    self->copyGridPotentialToHost();
   }
   return *impl->grid;
 }
-const std::vector<std::complex<float>>& PMMethod::getGridDensity() {
-  copyGridDensityToHost();
-  return impl->grid->densityStorage();
-}
-const std::vector<std::complex<float>>& PMMethod::getGridPotential() {
-  copyGridPotentialToHost();
-  return impl->grid->potentialStorage();
-}
+// include_gpu/PMMethodGPU.h:38-39: the vectors as of the last copyGrid*ToHost()
+const std::vector<std::complex<float>>& PMMethod::getGridDensity() const { return impl->gridDensity; }
+const std::vector<std::complex<float>>& PMMethod::getGridPotential() const { return impl->gridPotential; }
 
 // The shared body of PMMethod::run (source/pmMethod.cpp:62-135) and P3MMethod::run
 // (source/p3mMethod.cpp:59-166).
@@ -298,17 +296,22 @@ void PMMethod::runLoop(StateRecorder& rec, int simLength, bool diagnostics, bool
   check(p3m_green_init(s.ctx), "p3m_green_init");
   force();
   check(p3m_kick(s.ctx, 0.5f), "p3m_kick");  // setHalfStepVelocities
-  std::vector<float> buf(3 * n);
+  // only StateRecorder members the reference's class has too (include/stateRecorder.h:26-36): in
+  // reference-tree mode `rec` IS the reference's recorder
+  static_assert(sizeof(Vec3) == 3 * sizeof(float), "Vec3 is three packed floats");
+  std::vector<Vec3> posbuf(n);
+  float* buf = reinterpret_cast<float*>(posbuf.data());
   for (int t = 0; t <= simLength; ++t) {
     std::cout << "progress: " << float(t) / simLength << '\r';
     std::cout.flush();
     if (recordField) {
-      check(p3m_get_particles(s.ctx, nullptr, nullptr, buf.data(), P3M_UNITS_ORIGINAL), "p3m_get_particles");
-      rec.recordField(buf.data(), n);
+      s.deviceIsNewer = true;
+      s.download();  // accelerations in code units; recordField converts (source/stateRecorder.cpp:102-108)
+      rec.recordField(s.particles, H, DT);
     }
     check(p3m_drift(s.ctx), "p3m_drift");  // updatePositions (+ the unit round trip, + escape flag)
-    check(p3m_get_particles(s.ctx, buf.data(), nullptr, nullptr, P3M_UNITS_ORIGINAL), "p3m_get_particles");
-    rec.recordPositions(buf.data(), n);
+    check(p3m_get_particles(s.ctx, buf, nullptr, nullptr, P3M_UNITS_ORIGINAL), "p3m_get_particles");
+    rec.recordPositions(posbuf.begin(), posbuf.end());
     if (diagnostics) {
       double d[11];
       check(p3m_diagnostics(s.ctx, d), "p3m_diagnostics");
@@ -371,10 +374,14 @@ P3MMethod::P3MMethod(PMMethod& pm, std::tuple<float, float, float> compBoxSize, 
   prm.softening = softeningLength;
   prm.cloud_shape = (int)cloudShape;
   prm.use_sr_table = useSRForceTable ? 1 : 0;
-  // the reference converts the short-range diameter with the H passed here (source/p3mMethod.cpp:36)
-  // and the mesh one with PMMethod's (source/pmMethod.cpp:56); both are the same number in every demo
-  (void)particleDiameter;
-  (void)H;
+  // the reference keeps its own particleDiameter for the short-range reference force (source/p3mMethod.cpp:36)
+  // next to PMMethod's for the influence function (source/pmMethod.cpp:56): honoured when they differ
+  prm.sr_particle_diameter = particleDiameter == prm.particle_diameter ? 0.0f : particleDiameter;
+  // cutoff, diameter, softening and the chaining mesh are converted with the H passed here
+  // (source/p3mMethod.cpp:35-37, source/chainingMesh.cpp:13-15) while the particles are in PMMethod's code
+  // units: a different H is an inconsistent set-up in the reference too -- refused instead of ignored
+  if (H != pm.getH())
+    throw std::invalid_argument("P3MMethod: H differs from the H of the PMMethod it wraps");
 }
 
 void P3MMethod::forceStep() {

@@ -12,8 +12,8 @@
 #include "../../../include/p3m_b200.h"
 #include "../include/particle_simulation_b200.hpp"
 
-static constexpr float kPi = 3.14159265358979323846f;
 
+#if !P3M_B200_REFERENCE_TREE  // reference-tree mode: the reference's own vec3.cpp provides these
 // ---- Vec3 (include/vec3.h, source/vec3.cpp) ------------------------------------------------------------
 float Vec3::getMagnitude() const { return std::sqrt(x * x + y * y + z * z); }
 
@@ -25,11 +25,31 @@ char* Vec3::toString(char* singleBuf, std::size_t singleBufSize, char* vecBuf, s
   return vecBuf;
 }
 
-// ---- unit conversions (include/unitConversions.h:8-50, source/unitConversions.cpp:23-71) -----------------
-float densityToCodeUnits(float density, float DT, float G) { return DT * DT * 4 * kPi * G * density; }
-float densityToOriginalUnits(float density, float DT, float G) { return density / (DT * DT * 4 * kPi * G); }
-float massToCodeUnits(float m, float H, float DT, float G) { return DT * DT * 4 * kPi * G / (H * H * H) * m; }
-float massToOriginalUnits(float m, float H, float DT, float G) { return (H * H * H) / (DT * DT * 4 * kPi * G) * m; }
+#endif  // !P3M_B200_REFERENCE_TREE
+
+// ---- unit conversions (source/unitConversions.cpp:7-71) ---------------------------------------------------
+void stateToCodeUnits(std::vector<Vec3>& state, float H, float DT) {
+  const size_t n = state.size() / 2;  // [0, n) positions, [n, 2n) velocities
+  for (size_t i = 0; i < n; ++i) state[i] = positionToCodeUntits(state[i], H);
+  for (size_t i = n; i < state.size(); ++i) state[i] = velocityToCodeUntits(state[i], H, DT);
+}
+void stateToOriginalUnits(std::vector<Vec3>& state, float H, float DT) {
+  const size_t n = state.size() / 2;
+  for (size_t i = 0; i < n; ++i) state[i] = positionToOriginalUnits(state[i], H);
+  for (size_t i = n; i < state.size(); ++i) state[i] = velocityToOriginalUnits(state[i], H, DT);
+}
+void velocitiesToCodeUnits(std::vector<Vec3>& v, float H, float DT) {
+  for (auto& x : v) x = velocityToCodeUntits(x, H, DT);
+}
+void velocitiesToOriginalUnits(std::vector<Vec3>& v, float H, float DT) {
+  for (auto& x : v) x = velocityToOriginalUnits(x, H, DT);
+}
+void integerStepVelocitiesToOriginalUnits(std::vector<Particle>& ps, float H, float DT) {
+  for (auto& p : ps) p.integerStepVelocity = velocityToOriginalUnits(p.integerStepVelocity, H, DT);
+}
+void integerStepVelocitiesToCodeUnits(std::vector<Particle>& ps, float H, float DT) {
+  for (auto& p : ps) p.integerStepVelocity = velocityToCodeUntits(p.integerStepVelocity, H, DT);
+}
 
 void stateToCodeUnits(std::vector<Particle>& ps, float H, float DT) {
   for (auto& p : ps) p.position = positionToCodeUntits(p.position, H), p.velocity = velocityToCodeUntits(p.velocity, H, DT);
@@ -64,6 +84,7 @@ void LeapfrogStepper::doStep(std::vector<Particle>& x, float dt) {
   updateVelocities(x, dt);
 }
 
+#if !P3M_B200_REFERENCE_TREE  // reference-tree mode: the reference's externalFields.cpp stays in the build
 // ---- external fields (source/externalFields.cpp:4-24) ----------------------------------------------------
 Vec3 sphRadDecrField(Vec3 pos, Vec3 center, float R, float M, float G) {
   const Vec3 d = pos - center;
@@ -77,6 +98,7 @@ float sphRadDecrFieldPotential(Vec3 pos, Vec3 center, float R, float M, float G)
   const float u = r / R;
   return G * M / R * (-2 + u * u * (2 - u));
 }
+#endif  // !P3M_B200_REFERENCE_TREE
 
 // ---- single-mode Green functions (source/greensFunctions.cpp:122-220), evaluated in double ------------------
 static double sincd(double x) { return x == 0 ? 1.0 : std::sin(x) / x; }
@@ -254,10 +276,59 @@ float SimInfo::potentialEnergy(const Grid& grid, const std::vector<Particle>& ps
         internal += (double)densityToOriginalUnits(grid.getDensity(x, y, z), DT, G) *
                     (double)potentialToOriginalUnits(grid.getPotential(x, y, z), H, DT);
   double external = 0;
-  for (const auto& p : ps) external += p.mass * externalPotential(p.position);
+  if (externalPotential)
+    for (const auto& p : ps) external += p.mass * externalPotential(p.position);
   return (float)(0.5 * H * H * H * internal + external);
 }
+// the CUDA-build overload (include/simInfo.h:30-36, source/simInfo.cpp:72-92): density / potential vectors as
+// PMMethodGPU::getGridDensity / getGridPotential return them (real parts, code units)
+float SimInfo::potentialEnergy(const std::vector<std::complex<float>>& gridDensity,
+                               const std::vector<std::complex<float>>& gridPotential, const std::vector<Particle>& ps,
+                               std::function<float(Vec3)> externalPotential, float H, float DT, float G) {
+  double internal = 0;
+  const size_t M = std::min(gridDensity.size(), gridPotential.size());
+  for (size_t i = 0; i < M; ++i)
+    internal += (double)densityToOriginalUnits(gridDensity[i].real(), DT, G) *
+                (double)potentialToOriginalUnits(gridPotential[i].real(), H, DT);
+  double external = 0;
+  if (externalPotential)
+    for (const auto& p : ps) external += p.mass * externalPotential(p.position);
+  return (float)(0.5 * H * H * H * internal + external);
+}
+// state-vector overloads (source/simInfo.cpp:4-48): direct pair sum with the reference's fixed softening 0.01
+float SimInfo::potentialEnergy(std::vector<Vec3>::iterator posBegin, std::vector<Vec3>::iterator posEnd,
+                               const std::vector<float>& masses, float G) {
+  const float eps = 0.01f;
+  float pe = 0;
+  int i = 0;
+  for (auto a = posBegin; a != posEnd; ++a, ++i) {
+    int j = i + 1;
+    for (auto b = a + 1; b != posEnd; ++b, ++j)
+      pe += (-1) * G * masses[i] * masses[j] / std::sqrt((*a - *b).getMagnitudeSquared() + eps * eps);
+  }
+  return pe;
+}
+float SimInfo::kineticEnergy(std::vector<Vec3>::iterator vBegin, std::vector<Vec3>::iterator vEnd,
+                             const std::vector<float>& masses, float /*G*/) {
+  float ke = 0;
+  int i = 0;
+  for (auto v = vBegin; v != vEnd; ++v, ++i) ke += 0.5f * masses[i] * v->getMagnitudeSquared();
+  return ke;
+}
+Vec3 SimInfo::totalMomentum(std::vector<Vec3>::iterator vBegin, std::vector<Vec3>::iterator vEnd,
+                            const std::vector<float>& masses) {
+  Vec3 m = Vec3::zero();
+  int i = 0;
+  for (auto v = vBegin; v != vEnd; ++v, ++i) m += masses[i] * (*v);
+  return m;
+}
+void SimInfo::setInitialMomentum(const std::vector<Particle>& particles) { expectedMomentum = totalMomentum(particles); }
+Vec3 SimInfo::updateExpectedMomentum(Vec3 externalForce, float DT) {
+  expectedMomentum += DT * externalForce;
+  return expectedMomentum;
+}
 
+#if !P3M_B200_REFERENCE_TREE  // reference-tree mode: the reference's stateRecorder.cpp stays in the build
 // ---- StateRecorder (source/stateRecorder.cpp; formats read by script/load_data.py:15-37) ---------------------------
 StateRecorder::StateRecorder(int particlesCnt, int framesCnt, const std::filesystem::path& outputDirPath,
                              const char* positionsFile, const char* energyFile, const char* momentumFile,
@@ -309,3 +380,4 @@ std::string StateRecorder::flush() {
   for (std::ofstream* f : {&positions, &field, &energy, &momentum, &expectedMomentum, &angularMomentum}) f->flush();
   return dir.string();
 }
+#endif  // !P3M_B200_REFERENCE_TREE

@@ -30,7 +30,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_params_struct_layout_and_defaults():
     p = capi.default_params()
-    assert C.sizeof(p) == 116  # 29 four-byte fields, no padding
+    assert C.sizeof(p) == 120  # 30 four-byte fields, no padding
+    assert p.sr_particle_diameter == 0.0
     assert (p.assignment, p.fd_scheme, p.greens_function) == (capi.TSC, capi.TWO_POINT, capi.S1_OPTIMAL)
     assert p.use_sr_table == 1 and p.DT == 1.0 and p.device == -1 and p.unit_roundtrip == 1
 

@@ -1,0 +1,162 @@
+"""GPU parity at the sizes the benchmarks run (round-2 additions).
+
+  * BASELINE configs[0] at its LITERAL size -- `galaxy-sim-pm` (source/demos.cpp:729-777: 50 000-particle linear
+    disk from the reference's own sampler, mesh 128 x 128 x 64, TSC, 2-point, discrete Laplacian, bulge field)
+    plus the CIC / 64^3 label of BASELINE.json and the P3M variant (source/demos.cpp:897-951) -- against the
+    UNMODIFIED reference compiled in oracle/_ref;
+  * the PM-context kernels (k_deposit_pm, k_gather_pm, the 32-bit sort key, k_poisson_z<8|9>) at 256^3 with
+    2^22 particles and at 512^3 with 2^24 particles (BASELINE configs[2]) against the fp32 / fp64 oracle;
+  * every radix plan of the fused z pass against the ORACLE's Poisson solve (not only against cuFFT).
+Tolerances are north_star's: 1e-4 (fp32 path), 1e-6 (fp64 path); cell indices bit-exact."""
+import numpy as np
+import pytest
+
+import refapi
+from common import to_p3m
+from particlesimulation_b200 import capi, ics
+from refapi import Oracle, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL32, TOL64 = 1e-4, 1e-6
+needs_ref = pytest.mark.skipif(not refapi.have_ref(), reason="oracle/_ref not built")
+
+
+def galaxy_demo_inputs(ref, n=50000):
+    """DiskSamplerLinear(42).sample(center, rb, mb, rd, md, thickness, G, n) of the compiled reference
+    (source/demos.cpp:745-748); masses md / n."""
+    pos, vel = ref.sample_disk_linear(42, (30.0, 30.0, 15.0), 3.0, 60.0, 15.0, 15.0, 0.3, 4.5e-3, n)
+    mass = np.full(n, np.float32(15.0) / np.float32(n), np.float32)
+    return pos, vel, mass
+
+
+BULGE = dict(center=(30.0, 30.0, 15.0), R=3.0, M=60.0)
+
+
+@needs_ref
+@pytest.mark.parametrize("grid,is_", [((128, 128, 64), refapi.TSC), ((128, 128, 64), refapi.CIC),
+                                      ((64, 64, 64), refapi.CIC)],
+                         ids=["128x128x64-TSC", "128x128x64-CIC", "64^3-CIC"])
+def test_c1_literal_pm_vs_compiled_reference(grid, is_):
+    ref = refapi.Ref()
+    pos, vel, mass = galaxy_demo_inputs(ref)
+    box = (60.0, 60.0, 30.0) if grid[2] == 64 and grid[0] == 128 else (60.0, 60.0, 60.0)
+    if box[2] == 60.0:
+        pos = pos + np.array([0, 0, 15.0], np.float32)  # centre the disk in the cubic 64^3 box
+    ext = dict(BULGE, center=(30.0, 30.0, box[2] / 2))
+    p = refapi.make_params(len(mass), grid, box, is_=is_, gfunc=refapi.DISCRETE_LAPLACIAN, diameter=0.0, ext=ext)
+    r = ref.pm_force(p, pos, vel, mass)
+    with capi.Context(to_p3m(p, p3m=False)) as ctx:
+        ctx.set_particles(pos, vel, mass)
+        ctx.force()
+        rho, phi = ctx.density(), ctx.potential()
+        acc = ctx.get_particles(capi.UNITS_CODE, want=("acc",))[2]
+        gpos = ctx.get_particles(capi.UNITS_CODE, want=("pos",))[0]
+        mc, _, order = ctx.cells()
+        ctx.gradient()
+        field = ctx.field()
+    assert np.array_equal(gpos, r["pos_code"])
+    t = r["pos_code"].astype(np.int32)
+    assert np.array_equal(mc, t[:, 0] + t[:, 1] * p.nx + t[:, 2] * p.nx * p.ny), "mesh cells must be bit-exact"
+    assert np.array_equal(np.sort(order), np.arange(len(mass)))
+    assert rel_l2(rho, r["density"]) < TOL32
+    assert rel_l2(phi, r["potential"]) < TOL32
+    assert rel_l2(field, r["field"]) < TOL32
+    assert rel_l2(acc, r["acc"]) < TOL32
+
+
+@needs_ref
+def test_c1_literal_p3m_vs_compiled_reference():
+    """galaxy-sim-p3m (source/demos.cpp:897-951): S1-optimal influence function, a = 3H, re = 0.7a, eps = 1.5."""
+    ref = refapi.Ref()
+    pos, vel, mass = galaxy_demo_inputs(ref)
+    p = refapi.make_params(len(mass), (128, 128, 64), (60.0, 60.0, 30.0), gfunc=refapi.S1_OPTIMAL, softening=1.5,
+                           ext=BULGE)
+    r = ref.p3m_force(p, pos, vel, mass)
+    with capi.Context(to_p3m(p, p3m=True, zero_degenerate=True)) as ctx:
+        ctx.set_particles(pos, vel, mass)
+        ctx.force()
+        acc = ctx.get_particles(capi.UNITS_CODE, want=("acc",))[2]
+        pm, sr = ctx.acc_parts()
+        _, cc, _ = ctx.cells()
+        dims = ctx.chaining_dims()
+    assert np.array_equal(dims, r["dims"])
+    assert np.array_equal(cc, r["cell"]), "chaining cells must be bit-exact"
+    assert rel_l2(pm, r["acc_pm"]) < TOL32
+    mcode = Oracle("f32").to_code_units(p, pos, vel, mass)[2]
+    assert rel_l2(sr * mcode[:, None].astype(np.float64), r["sr_force"]) < TOL32
+    assert rel_l2(acc, r["acc"]) < TOL32
+
+
+def uniform_pm_case(grid, n):
+    f32 = np.float32
+    H = float(f32(60.0) / f32(grid // 2))
+    pos, vel, mass = ics.uniform_cube(n, [2 * H] * 3, [60.0 - 2 * H] * 3, total_mass=1.0, seed=42)
+    p = refapi.make_params(n, (grid,) * 3, (60.0, 60.0, 60.0), gfunc=refapi.DISCRETE_LAPLACIAN)
+    return p, pos, vel, mass
+
+
+def check_pm_context(p, pos, vel, mass, precisions):
+    for prec, precision, tol in precisions:
+        o = Oracle(prec)
+        pc, _, mcode = o.to_code_units(p, pos, vel, mass)
+        rho_ref, phi_ref, acc_ref = o.force(p, False, o.green(p), pc, mcode)
+        with capi.Context(to_p3m(p, p3m=False, precision=precision)) as ctx:
+            ctx.set_particles(pos, vel, mass)
+            ctx.force()
+            f64 = precision == capi.F64
+            rho, phi = ctx.density(f64=f64), ctx.potential(f64=f64)
+            gpos, _, acc = ctx.get_particles(capi.UNITS_CODE, f64=f64)
+            mc, _, order = ctx.cells()
+            info = ctx.binning()
+        assert info["p3m"] == 0 and info["sbits"] == 3, "PM context: (8^3 tile, mesh cell) sort key"
+        if prec == "f32":
+            assert np.array_equal(gpos, pc)
+            t = pc.astype(np.int32)
+            cell = t[:, 0].astype(np.int64) + t[:, 1].astype(np.int64) * p.nx + t[:, 2].astype(np.int64) * p.nx * p.ny
+            assert np.array_equal(mc.astype(np.int64), cell), "mesh cells must be bit-exact"
+            # sort order: non-decreasing (Morton(8^3 tile), mesh cell in the tile)
+            from common import morton3
+            key = (morton3(t[:, 0] >> 3, t[:, 1] >> 3, t[:, 2] >> 3) << np.uint64(9)) | \
+                  ((t[:, 2] & 7).astype(np.uint64) << np.uint64(6)) | ((t[:, 1] & 7).astype(np.uint64) << np.uint64(3)) | \
+                  (t[:, 0] & 7).astype(np.uint64)
+            assert np.all(np.diff(key[order].astype(np.int64)) >= 0)
+            assert np.array_equal(np.sort(order), np.arange(len(mass)))
+        assert rel_l2(rho, rho_ref) < tol, prec
+        assert rel_l2(phi, phi_ref) < tol, prec
+        assert rel_l2(acc, acc_ref) < tol, prec
+
+
+def test_pm_context_kernels_256_vs_oracle():
+    """2^22 uniform particles on 256^3: k_deposit_pm, k_poisson_z<8>, k_gather_pm, 32-bit key vs the oracle."""
+    p, pos, vel, mass = uniform_pm_case(256, 1 << 22)
+    check_pm_context(p, pos, vel, mass, [("f32", capi.F32, TOL32), ("f64", capi.F64, TOL64)])
+
+
+@pytest.mark.slow
+def test_pm_context_kernels_512_vs_oracle():
+    """BASELINE configs[2] on one GPU: 2^24 uniform particles on 512^3 (k_poisson_z<9>) vs the fp32 oracle
+    (~1.5 min of host time for the oracle's own solve)."""
+    p, pos, vel, mass = uniform_pm_case(512, 1 << 24)
+    check_pm_context(p, pos, vel, mass, [("f32", capi.F32, TOL32)])
+
+
+@pytest.mark.parametrize("precision,prec,tol", [(capi.F32, "f32", 5e-6), (capi.F64, "f64", 1e-11)])
+@pytest.mark.parametrize("nz", [16, 32, 64, 128, 256, 512, 1024])
+def test_fused_z_pass_every_plan_vs_oracle(nz, precision, prec, tol):
+    """k_poisson_z, every radix plan 2^4..2^10, against the oracle's Poisson solve (its own mixed-radix C2C FFT
+    + multiply + .real(), source/grid.cpp:50-68, source/pmMethod.cpp:340-350) on the same density."""
+    grid = (8, 4, nz)
+    box = (60.0, 30.0, 60.0 * nz / 8)
+    p = refapi.make_params(16, grid, box, gfunc=refapi.DISCRETE_LAPLACIAN)
+    rng = np.random.default_rng(nz)
+    rho = rng.standard_normal((nz, grid[1], grid[0])).astype(np.float32)
+    o = Oracle("f64")
+    phi_ref = o.poisson(p, rho.astype(np.float64), o.green(p))
+    with capi.Context(to_p3m(p, p3m=False, precision=precision)) as ctx:
+        assert ctx.fused_z
+        ctx.green_init()
+        ctx.set_density(rho)
+        ctx.poisson()
+        phi = ctx.potential(f64=True)
+    assert rel_l2(phi, phi_ref) < tol
