@@ -136,6 +136,37 @@ int p3m_rank_info(p3m_ctx* ctx, int64_t out[8]);
  * (source/PMMethodGPU.cu:241-247). */
 int p3m_set_particles(p3m_ctx* ctx, const float* pos, const float* vel, const float* mass,
                       int64_t n, int units);
+/* ---- N3: initial conditions generated ON THE DEVICE ---------------------------------
+ * The DISTRIBUTIONS of the reference's samplers -- PlummerSampler::sample (source/plummerSampler.cpp:11-83),
+ * DiskSamplerLinear::sample (source/diskSamplerLinear.cpp:10-74), a uniform cube (BASELINE configs[2]) and the
+ * clustered disk + halo mix of configs[3] -- from a COUNTER-BASED generator: particle i of a set is a pure
+ * function of (seed, i), so every rank can produce exactly its own share and any index range can be re-created
+ * anywhere.  (The reference's own random streams are implementation-defined, SURVEY Q11: the distributions are
+ * reproduced, not the streams.)  Quantities are in ORIGINAL units, as the samplers' callers pass them. */
+enum { P3M_IC_PLUMMER = 0, P3M_IC_DISK_LINEAR = 1, P3M_IC_UNIFORM = 2, P3M_IC_DISK_HALO = 3 };
+typedef struct p3m_ic {
+  int32_t kind;
+  int32_t truncate;      /* Plummer radii beyond r_max: 0 = moved onto the r_max shell as the reference does
+                            (source/plummerSampler.cpp:50-52), 1 = the CDF is truncated at r_max (no shell) */
+  uint64_t seed;
+  int64_t n;             /* particles of the whole set (all ranks together) */
+  float center[3];
+  float total_mass;      /* every particle gets total_mass / n (the reference's callers: masses(n, M / n)) */
+  float G;
+  float a, r_max;        /* PLUMMER: scale radius, cut radius; DISK_HALO: the halo's */
+  float rb, mb, rd, md, thickness, r0; /* DISK_LINEAR: bulge radius / mass, disk radius / mass, thickness, inner
+                                          radius; DISK_HALO: rd, thickness of its disk (in the x-z plane) */
+  float lo[3], hi[3];    /* UNIFORM: positions in [lo, hi) */
+  float vel_sigma;       /* UNIFORM: isotropic Gaussian velocity dispersion (0 = at rest) */
+} p3m_ic;
+/* Fills the context with the set: replaces p3m_set_particles.  With several ranks the call is collective-free:
+ * every rank evaluates the per-layer work weights of the whole set on its own device (identical results), derives
+ * the same work-balanced cuts, and keeps the particles of its own z-slab -- no host array, no full upload. */
+int p3m_generate_particles(p3m_ctx* ctx, const p3m_ic* ic);
+/* Particles [first, first + count) of the set as packed host arrays (any pointer may be NULL); needs a CUDA
+ * device but no context.  Used by the tests and to feed the same set to the CPU reference. */
+int p3m_sample_particles(const p3m_ic* ic, int64_t first, int64_t count, float* pos, float* vel, float* mass);
+
 /* Download in original particle order; any pointer may be NULL.  acc is always in code units when
  * units == P3M_UNITS_CODE, else converted with accelerationToOriginalUnits.  Replaces
  * getParticles() / copyParticlesDeviceToHost (source/PMMethodGPU.cu:244-247). */
@@ -229,6 +260,26 @@ int p3m_chaining_neighbors(const int32_t dims[3], int32_t cell, int32_t out14[14
 /* mesh part of the acceleration and short-range acceleration (= total SR force / mass), code units */
 int p3m_get_acc_parts(p3m_ctx* ctx, double* acc_pm, double* acc_sr);
 int p3m_get_sr_table(p3m_ctx* ctx, double* table500);
+/* rows of a SAMPLE of particles, by global id (ids ascending): code-unit position, total acceleration and its
+ * short-range part, 3 doubles each (any output may be NULL).  Rows of particles this rank does not hold are
+ * zero, so the sum over ranks is the full answer.  For parity figures at sizes where id-indexed readbacks of
+ * the whole set are not wanted (bench.py). */
+int p3m_get_sample(p3m_ctx* ctx, const int32_t* ids_ascending, int64_t m, double* pos, double* acc, double* acc_sr);
+
+/* ---- N4: brute-force accuracy oracle on the device ------------------------------
+ * Double-precision sums over ALL particles this rank holds, for `m` target points given in code units -- no
+ * chaining mesh, no sort order, no culling, no table replication: an independent evaluation of what the
+ * short-range kernels compute, and the O(N^2) reference the thesis' accuracy experiments compare P3M with
+ * (source/ppMethod.cpp:88-125 `ppMethodLeapfrog`, source/demos.cpp:593-727, script/p3m_accuracy.py:32-36).
+ *   P3M_SUM_SHORT_RANGE  a_i = sum_j m_j f(r_ij) r_ij over r_ij < cutoff, f = the context's short-range law
+ *                        (tabulated, source/p3mMethod.cpp:240-245, or analytic, :220-238)
+ *   P3M_SUM_NEWTON       a_i = -G_c sum_j m_j r_ij / (r_ij^2 + eps^2)^(3/2), G_c = 1/(4 pi): softened Newtonian
+ *                        gravity in code units (source/ppMethod.cpp:100-113 with G -> G_c)
+ * Pairs at zero distance are skipped (a target that is one of the particles does not attract itself).
+ * Multi-GPU: every rank returns the contribution of its own particles; the caller adds the ranks up. */
+enum { P3M_SUM_SHORT_RANGE = 0, P3M_SUM_NEWTON = 1 };
+int p3m_direct_sum(p3m_ctx* ctx, int mode, const double* target_pos_code, int64_t m, double softening_code,
+                   double* acc_code);
 
 /* ---- measurement -------------------------------------------------------------------------- */
 #define P3M_NPHASE 10

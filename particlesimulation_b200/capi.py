@@ -44,6 +44,59 @@ class P3MParams(C.Structure):
     ]
 
 
+IC_PLUMMER, IC_DISK_LINEAR, IC_UNIFORM, IC_DISK_HALO = 0, 1, 2, 3
+SUM_SHORT_RANGE, SUM_NEWTON = 0, 1
+
+
+class P3MIc(C.Structure):
+    """struct p3m_ic (include/p3m_b200.h): device-side initial conditions."""
+
+    _fields_ = [
+        ("kind", C.c_int32), ("truncate", C.c_int32), ("seed", C.c_uint64), ("n", C.c_int64),
+        ("center", C.c_float * 3), ("total_mass", C.c_float), ("G", C.c_float),
+        ("a", C.c_float), ("r_max", C.c_float),
+        ("rb", C.c_float), ("mb", C.c_float), ("rd", C.c_float), ("md", C.c_float), ("thickness", C.c_float),
+        ("r0", C.c_float),
+        ("lo", C.c_float * 3), ("hi", C.c_float * 3), ("vel_sigma", C.c_float),
+    ]
+
+
+def ic_plummer(n, center=(30.0, 30.0, 30.0), a=2.0, r_max=15.0, M=1.0, G=4.5e-3, seed=42, truncate=False):
+    ic = P3MIc(kind=IC_PLUMMER, truncate=int(truncate), seed=seed, n=n, total_mass=M, G=G, a=a, r_max=r_max)
+    ic.center[:] = center
+    return ic
+
+
+def ic_disk_linear(n, center=(30.0, 30.0, 15.0), rb=3.0, mb=60.0, rd=15.0, md=15.0, thickness=0.3, G=4.5e-3, seed=42,
+                   r0=0.0):
+    ic = P3MIc(kind=IC_DISK_LINEAR, seed=seed, n=n, total_mass=md, G=G, rb=rb, mb=mb, rd=rd, md=md,
+               thickness=thickness, r0=r0)
+    ic.center[:] = center
+    return ic
+
+
+def ic_uniform(n, lo, hi, total_mass=1.0, vel_sigma=0.0, seed=42):
+    ic = P3MIc(kind=IC_UNIFORM, seed=seed, n=n, total_mass=total_mass, vel_sigma=vel_sigma)
+    ic.lo[:] = lo
+    ic.hi[:] = hi
+    return ic
+
+
+def ic_disk_halo(n, box=60.0, halo_a=12.0, halo_rmax=27.0, disk_rd=24.0, thickness=3.0, M=1.0, G=4.5e-3, seed=42):
+    ic = P3MIc(kind=IC_DISK_HALO, truncate=1, seed=seed, n=n, total_mass=M, G=G, a=halo_a, r_max=halo_rmax,
+               rd=disk_rd, thickness=thickness)
+    ic.center[:] = (box / 2,) * 3
+    return ic
+
+
+def sample_particles(ic, first=0, count=None):
+    """Particles [first, first + count) of a device-generated set as host arrays (needs a GPU, no context)."""
+    count = int(ic.n - first if count is None else count)
+    pos = np.empty((count, 3), np.float32); vel = np.empty((count, 3), np.float32); mass = np.empty(count, np.float32)
+    _check(lib().p3m_sample_particles(C.byref(ic), int(first), count, _p(pos), _p(vel), _p(mass)))
+    return pos, vel, mass
+
+
 class P3MError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"p3m error {code}: {msg}")
@@ -57,15 +110,15 @@ SYMBOLS = [
     "p3m_last_error", "p3m_version", "p3m_default_params", "p3m_create", "p3m_destroy",
     "p3m_comm_unique_id", "p3m_create_dist", "p3m_get_local", "p3m_set_particles_ids", "p3m_num_global",
     "p3m_rank_info", "p3m_slab_cuts", "p3m_balanced_cuts",
-    "p3m_set_particles", "p3m_get_particles", "p3m_get_particles_f64", "p3m_num_particles",
+    "p3m_generate_particles", "p3m_sample_particles", "p3m_set_particles", "p3m_get_particles", "p3m_get_particles_f64", "p3m_num_particles",
     "p3m_green_init", "p3m_set_green_table", "p3m_set_green_table_f64", "p3m_get_green_table",
     "p3m_bin_sort", "p3m_deposit", "p3m_poisson", "p3m_gradient", "p3m_gather", "p3m_short_range",
     "p3m_force", "p3m_kick", "p3m_drift", "p3m_step", "p3m_escaped", "p3m_diagnostics",
     "p3m_add_acceleration", "p3m_fft3d_c2c",
     "p3m_get_density", "p3m_get_potential", "p3m_get_field", "p3m_get_density_f64",
     "p3m_get_potential_f64", "p3m_set_density", "p3m_set_potential", "p3m_get_cells",
-    "p3m_get_chaining_dims", "p3m_get_binning", "p3m_chaining_neighbors", "p3m_get_acc_parts", "p3m_get_sr_table",
-    "p3m_get_phase_ms", "p3m_phase_name", "p3m_get_pair_counts", "p3m_get_stats", "p3m_launch_count", "p3m_stream",
+    "p3m_get_chaining_dims", "p3m_get_binning", "p3m_chaining_neighbors", "p3m_get_acc_parts", "p3m_get_sr_table", "p3m_get_sample",
+    "p3m_get_phase_ms", "p3m_phase_name", "p3m_get_pair_counts", "p3m_get_stats", "p3m_direct_sum", "p3m_launch_count", "p3m_stream",
     "p3m_synchronize",
 ]
 
@@ -111,6 +164,10 @@ def lib():
         L.p3m_get_pair_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.p3m_get_phase_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.p3m_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.p3m_get_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.p3m_direct_sum.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_void_p]
+        L.p3m_generate_particles.argtypes = [C.c_void_p, C.c_void_p]
+        L.p3m_sample_particles.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.p3m_chaining_neighbors.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         _lib = L
     return _lib
@@ -238,6 +295,10 @@ class Context:
         mass = np.ascontiguousarray(mass, np.float32); ids = np.ascontiguousarray(ids, np.int32)
         _check(lib().p3m_set_particles_ids(self._h, _p(pos), _p(vel), _p(mass), _p(ids), len(ids), units))
 
+    def generate_particles(self, ic):
+        """Device-side initial conditions (p3m_generate_particles): every rank keeps its own z-slab."""
+        _check(lib().p3m_generate_particles(self._h, C.byref(ic)))
+
     def set_particles(self, pos, vel, mass, units=UNITS_ORIGINAL):
         pos = np.ascontiguousarray(pos, np.float32)
         mass = np.ascontiguousarray(mass, np.float32)
@@ -341,6 +402,14 @@ class Context:
         _check(lib().p3m_get_acc_parts(self._h, _p(pm), _p(sr)))
         return pm, sr
 
+    def sample(self, ids):
+        """(pos, acc, acc_sr) rows, code units, of the particles with the given ascending global ids (zeros where
+        this rank does not hold the particle)."""
+        ids = np.ascontiguousarray(ids, np.int32)
+        out = [np.zeros((len(ids), 3), np.float64) for _ in range(3)]
+        _check(lib().p3m_get_sample(self._h, _p(ids), len(ids), _p(out[0]), _p(out[1]), _p(out[2])))
+        return out
+
     def sr_table(self):
         t = np.empty(500, np.float64)
         _check(lib().p3m_get_sr_table(self._h, _p(t)))
@@ -355,6 +424,13 @@ class Context:
         a = C.c_uint64(0); b = C.c_uint64(0)
         _check(lib().p3m_get_pair_counts(self._h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
+
+    def direct_sum(self, target_pos_code, mode=0, softening_code=0.0):
+        """N4: fp64 brute-force sum over this rank's particles for the given target points (code units)."""
+        t = np.ascontiguousarray(target_pos_code, np.float64).reshape(-1, 3)
+        out = np.zeros_like(t)
+        _check(lib().p3m_direct_sum(self._h, int(mode), _p(t), len(t), float(softening_code), _p(out)))
+        return out
 
     STAT_NAMES = ("fused_z", "slab", "uniform_mass_table", "packed_pp", "incremental_sort", "migrated", "ghosts",
                   "a2a_bytes", "density_plane_bytes", "potential_plane_bytes", "migration_bytes", "ghost_bytes",

@@ -38,18 +38,48 @@ void p3m_tune_load_impl(p3m_tune& t) {
   if (const char* e = getenv("P3M_TUNE_A2A_CHUNKS")) t.a2a_chunks = atoi(e);
 }
 
+static cudaEvent_t timer_event(PhaseTimer& t) {
+  if (!t.pool.empty()) {
+    cudaEvent_t e = t.pool.back();
+    t.pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
 void phase_begin(p3m_ctx* c, int ph) {
   if (!c->timing) return;
-  cudaEventRecord(c->timer.a[ph], c->stream);
+  PhaseTimer& t = c->timer;
+  if (t.cur[ph]) t.pool.push_back(t.cur[ph]);  // begin without end: drop
+  t.cur[ph] = timer_event(t);
+  cudaEventRecord(t.cur[ph], c->stream);
 }
 
 void phase_end(p3m_ctx* c, int ph) {
   if (!c->timing) return;
-  cudaEventRecord(c->timer.b[ph], c->stream);
-  // resolved lazily: accumulate now (synchronising keeps the accounting simple; timing mode only)
-  cudaEventSynchronize(c->timer.b[ph]);
-  float ms = 0;
-  if (cudaEventElapsedTime(&ms, c->timer.a[ph], c->timer.b[ph]) == cudaSuccess) c->timer.acc_ms[ph] += ms;
+  PhaseTimer& t = c->timer;
+  if (!t.cur[ph]) return;
+  cudaEvent_t b = timer_event(t);
+  cudaEventRecord(b, c->stream);
+  t.open_.push_back(PhaseTimer::Interval{ph, t.cur[ph], b});
+  t.cur[ph] = nullptr;
+  if (t.open_.size() > 4096) phase_resolve(c);  // bound the pool on very long runs
+}
+
+// fold every recorded interval into acc_ms (synchronises the stream once)
+void phase_resolve(p3m_ctx* c) {
+  PhaseTimer& t = c->timer;
+  if (t.open_.empty()) return;
+  cudaStreamSynchronize(c->stream);
+  for (const PhaseTimer::Interval& iv : t.open_) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, iv.a, iv.b) == cudaSuccess) t.acc_ms[iv.ph] += ms;
+    t.pool.push_back(iv.a);
+    t.pool.push_back(iv.b);
+  }
+  t.open_.clear();
 }
 
 template <typename T> int escaped_now(p3m_ctx* c, int* escaped);
@@ -205,11 +235,6 @@ static int create_common(const p3m_params* prm, const void* uid, int rank, int n
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
   }
-  memset(&c->timer, 0, sizeof(c->timer));
-  for (int i = 0; i < P3M_NPHASE; ++i) {
-    cudaEventCreate(&c->timer.a[i]);
-    cudaEventCreate(&c->timer.b[i]);
-  }
   {
     // massToCodeUnits factor, left to right as include/unitConversions.h:42-44
     const float DT = prm->DT, H = prm->H, G = prm->G, pi = 3.14159265358979323846f;
@@ -319,10 +344,10 @@ int p3m_destroy(p3m_ctx* c) {
   dist_destroy(c);
   free_state<float>(c);
   free_state<double>(c);
-  for (int i = 0; i < P3M_NPHASE; ++i) {
-    if (c->timer.a[i]) cudaEventDestroy(c->timer.a[i]);
-    if (c->timer.b[i]) cudaEventDestroy(c->timer.b[i]);
-  }
+  phase_resolve(c);
+  for (cudaEvent_t e : c->timer.pool) cudaEventDestroy(e);
+  for (int i = 0; i < P3M_NPHASE; ++i)
+    if (c->timer.cur[i]) cudaEventDestroy(c->timer.cur[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -348,6 +373,17 @@ int p3m_set_particles(p3m_ctx* c, const float* pos, const float* vel, const floa
     P3M_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 4, c->stream));
   }
   return r;
+}
+
+static_assert(sizeof(p3m_ic) == 104 && sizeof(p3m_params) == 120, "ABI structs are mirrored by ctypes (capi.py)");
+
+int p3m_generate_particles(p3m_ctx* c, const p3m_ic* ic) {
+  CHECK_CTX(c);
+  return P3M_DISPATCH(c, generate_particles, ic);
+}
+
+int p3m_sample_particles(const p3m_ic* ic, int64_t first, int64_t count, float* pos, float* vel, float* mass) {
+  return sample_particles(ic, (long long)first, (long long)count, pos, vel, mass);
 }
 
 int p3m_get_particles(p3m_ctx* c, float* pos, float* vel, float* acc, int units) {
@@ -574,6 +610,17 @@ int p3m_get_acc_parts(p3m_ctx* c, double* acc_pm, double* acc_sr) {
   return P3M_DISPATCH(c, get_acc_parts, acc_pm, acc_sr);
 }
 
+int p3m_get_sample(p3m_ctx* c, const int32_t* ids, int64_t m, double* pos, double* acc, double* acc_sr) {
+  CHECK_CTX(c);
+  if (!c->have_particles) return fail(P3M_ESTATE, "no particles set");
+  if (m < 0 || (m > 0 && !ids)) return fail(P3M_EINVAL, "p3m_get_sample: bad argument");
+  for (int64_t k = 1; k < m; ++k)
+    if (ids[k] <= ids[k - 1]) return fail(P3M_EINVAL, "p3m_get_sample: ids must be strictly ascending");
+  if ((acc || acc_sr) && c->n > 0 && !c->have_acc)
+    return fail(P3M_ESTATE, "p3m_get_sample: accelerations are stale (re-sorted since the last p3m_gather)");
+  return P3M_DISPATCH(c, get_sample, ids, (long long)m, pos, acc, acc_sr);
+}
+
 int p3m_get_sr_table(p3m_ctx* c, double* t) {
   if (!c || !t) return fail(P3M_EINVAL, "null argument");
   if (c->sr_table_host.size() != kSRTable) return fail(P3M_ESTATE, "no short-range table (PM-only context)");
@@ -589,6 +636,7 @@ const char* p3m_phase_name(int i) { return (i >= 0 && i < P3M_NPHASE) ? kPhaseNa
 
 int p3m_get_phase_ms(p3m_ctx* c, float ms[P3M_NPHASE], int reset) {
   if (!c) return fail(P3M_EINVAL, "null context");
+  phase_resolve(c);
   for (int i = 0; i < P3M_NPHASE; ++i) {
     ms[i] = c->timer.acc_ms[i];
     if (reset) c->timer.acc_ms[i] = 0;
@@ -612,6 +660,15 @@ int p3m_get_pair_counts(p3m_ctx* c, uint64_t* checked, uint64_t* in_range) {
   if (checked) *checked = h[0];
   if (in_range) *in_range = h[1];
   return 0;
+}
+
+int p3m_direct_sum(p3m_ctx* c, int mode, const double* tpos, int64_t m, double eps, double* out) {
+  CHECK_CTX(c);
+  if (!c->have_particles) return fail(P3M_ESTATE, "no particles set");
+  if (m < 0 || (m > 0 && (!tpos || !out))) return fail(P3M_EINVAL, "p3m_direct_sum: bad argument");
+  if (mode != P3M_SUM_SHORT_RANGE && mode != P3M_SUM_NEWTON) return fail(P3M_EINVAL, "p3m_direct_sum: unknown mode %d", mode);
+  if (mode == P3M_SUM_SHORT_RANGE && !c->prm.p3m) return fail(P3M_ESTATE, "p3m_direct_sum: PM-only context has no short-range law");
+  return P3M_DISPATCH(c, direct_sum, mode, tpos, (long long)m, eps, out);
 }
 
 int p3m_get_stats(p3m_ctx* c, double out[P3M_NSTAT]) {

@@ -7,10 +7,15 @@
 
 namespace p3m {
 
+// Per-phase CUDA-event timing that never blocks the host: phase_begin / phase_end only RECORD events (taken
+// from a pool) on the context's stream; p3m_get_phase_ms synchronises once and folds every recorded interval
+// into acc_ms.  Enabling it therefore does not serialise host and device between phases.
 struct PhaseTimer {
-  cudaEvent_t a[P3M_NPHASE], b[P3M_NPHASE];
-  float acc_ms[P3M_NPHASE];
-  bool pending[P3M_NPHASE];
+  struct Interval { int ph; cudaEvent_t a, b; };
+  std::vector<Interval> open_;      // recorded, not yet resolved
+  std::vector<cudaEvent_t> pool;    // free events
+  cudaEvent_t cur[P3M_NPHASE] = {};  // begin event of a phase that has not ended yet
+  float acc_ms[P3M_NPHASE] = {};
 };
 
 template <typename T>
@@ -174,6 +179,7 @@ enum Phase {
 
 void phase_begin(p3m_ctx* c, int ph);
 void phase_end(p3m_ctx* c, int ph);
+void phase_resolve(p3m_ctx* c);
 
 // implemented one per .cu file, templated on the arithmetic type
 template <typename T> int alloc_particles(p3m_ctx* c, long long n);
@@ -197,6 +203,7 @@ template <typename T> int diagnostics(p3m_ctx* c, double* out);
 template <typename T> int escaped_now(p3m_ctx* c, int* escaped);
 template <typename T> int get_cells(p3m_ctx* c, int32_t* mesh_cell, int32_t* chain_cell, int32_t* order);
 template <typename T> int get_acc_parts(p3m_ctx* c, double* acc_pm, double* acc_sr);
+template <typename T> int get_sample(p3m_ctx* c, const int32_t* ids, long long m, double* pos, double* acc, double* acc_sr);
 template <typename T> int add_acceleration(p3m_ctx* c, const float* a, int units);
 int fft3d_c2c(int nz, int ny, int nx, const float* in, float* out, int inverse);
 // dist.cu
@@ -218,6 +225,12 @@ template <typename T> void slab_free(p3m_ctx* c);
 template <typename T> int slab_replan(p3m_ctx* c);           // after the layer cuts moved
 // dist.cu: equal-COUNT layer cuts from the full particle set every rank was handed (clustered sets)
 template <typename T> int dist_balance_cuts(p3m_ctx* c, const float* pos, long long n, int units);
+template <typename T> int dist_cuts_from_weights(p3m_ctx* c, const double* weight, int layers);  // + slab_replan
+// ics.cu: device-side initial conditions
+template <typename T> int generate_particles(p3m_ctx* c, const p3m_ic* ic);
+int sample_particles(const p3m_ic* ic, long long first, long long count, float* pos, float* vel, float* mass);
+// directsum.cu: N4 brute-force accuracy oracle
+template <typename T> int direct_sum(p3m_ctx* c, int mode, const double* tpos, long long m, double eps, double* out);
 template <typename T> int slab_reduce_density(p3m_ctx* c);    // dens_part of all ranks -> density slabs
 template <typename T> int slab_poisson(p3m_ctx* c);           // distributed FFT Poisson solve
 template <typename T> int slab_spread_potential(p3m_ctx* c);  // potential slabs -> pot_part of all ranks

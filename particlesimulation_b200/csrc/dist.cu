@@ -60,7 +60,7 @@ static void set_cuts(p3m_ctx* c) {
     if (layers < P) layers = g.mz;
   }
   g.nranks = P, g.rank = c->rank;
-  for (int r = 0; r <= 8; ++r) g.cut[r] = (int)(((long long)(r < P ? r : P) * layers) / P);
+  for (int r = 0; r <= P3M_MAX_RANKS; ++r) g.cut[r] = (int)(((long long)(r < P ? r : P) * layers) / P);
   g.lay0 = g.cut[c->rank];
   g.lay1 = c->rank == P - 1 ? 0x7fffffff : g.cut[c->rank + 1];
   if (c->rank == 0) g.lay0 = -0x7fffffff;
@@ -75,6 +75,9 @@ static void set_cuts(p3m_ctx* c) {
 // cut[r] = first layer at which the cumulative weight reaches r/P of the total, kept strictly increasing so that
 // every rank owns at least one layer.  A single layer is never split, so a structure thinner than one layer
 // along z still lands on one rank.
+template <typename T>
+int dist_cuts_from_weights(p3m_ctx* c, const double* weight, int layers);
+
 template <typename T>
 int dist_balance_cuts(p3m_ctx* c, const float* pos, long long n, int units) {
   if (c->nranks <= 1 || n <= 0 || c->tune.static_cuts) return 0;
@@ -127,24 +130,32 @@ int dist_balance_cuts(p3m_ctx* c, const float* pos, long long n, int units) {
       weight[(size_t)z] = w;
     }
   }
+  return dist_cuts_from_weights<T>(c, weight.data(), layers);
+}
+
+// cut[r] = first layer at which the cumulative weight reaches r/P of the total (see dist_balance_cuts)
+template <typename T>
+int dist_cuts_from_weights(p3m_ctx* c, const double* weight, int layers) {
+  Geom<T>& g = Sel<T>::g(c);
+  const int P = c->nranks;
   double total = 0.0;
-  for (double w : weight) total += w;
-  int cut[9];
+  for (int z = 0; z < layers; ++z) total += weight[z];
+  int cut[P3M_MAX_RANKS + 1];
   cut[0] = 0;
   double cum = 0.0;
   int l = 0;
   for (int r = 1; r < P; ++r) {
     const double want = total * r / P;
-    while (l < layers && cum + weight[(size_t)l] <= want) cum += weight[(size_t)l++];
+    while (l < layers && cum + weight[l] <= want) cum += weight[l++];
     // the layer holding the quantile goes to whichever side leaves the smaller excess
     int k = l;
-    if (l < layers && want - cum > cum + weight[(size_t)l] - want) k = l + 1;
+    if (l < layers && want - cum > cum + weight[l] - want) k = l + 1;
     if (k <= cut[r - 1]) k = cut[r - 1] + 1;
     if (k > layers - (P - r)) k = layers - (P - r);
     cut[r] = k;
   }
-  for (int r = P; r <= 8; ++r) cut[r] = layers;
-  for (int r = 0; r <= 8; ++r) g.cut[r] = cut[r];
+  for (int r = P; r <= P3M_MAX_RANKS; ++r) cut[r] = layers;
+  for (int r = 0; r <= P3M_MAX_RANKS; ++r) g.cut[r] = cut[r];
   g.lay0 = c->rank == 0 ? -0x7fffffff : g.cut[c->rank];
   g.lay1 = c->rank == P - 1 ? 0x7fffffff : g.cut[c->rank + 1];
   return slab_replan<T>(c);
@@ -470,6 +481,8 @@ int dist_ghosts(p3m_ctx* c) {
   return 0;
 }
 
+template int dist_cuts_from_weights<float>(p3m_ctx*, const double*, int);
+template int dist_cuts_from_weights<double>(p3m_ctx*, const double*, int);
 template int dist_balance_cuts<float>(p3m_ctx*, const float*, long long, int);
 template int dist_balance_cuts<double>(p3m_ctx*, const float*, long long, int);
 template int dist_migrate<float>(p3m_ctx*, bool);

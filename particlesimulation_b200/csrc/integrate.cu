@@ -85,10 +85,14 @@ int drift(p3m_ctx* c) {
                                                                      s.flags, s.flags + 3);
     P3M_LAUNCH_CHECK(c);
   }
-  P3M_TRY(dist_allreduce(c, s.flags + 3, 1, 0));  // every rank must take the same decision
+  phase_end(c, PH_INTEGRATE);
+  if (c->nranks > 1) {  // every rank must take the same decision; the wait for the slowest rank is `comm` time
+    phase_begin(c, PH_COMM);
+    P3M_TRY(dist_allreduce(c, s.flags + 3, 1, 0));
+    phase_end(c, PH_COMM);
+  }
   k_publish_escape<<<1, 1, 0, c->stream>>>(s.flags);
   P3M_LAUNCH_CHECK(c);
-  phase_end(c, PH_INTEGRATE);
   c->sorted = false;
   return 0;
 }
@@ -240,6 +244,60 @@ int get_acc_parts(p3m_ctx* c, double* acc_pm, double* acc_sr) {
   return 0;
 }
 
+// rows of the particles whose id is in the ascending list `ids` (binary search per local particle)
+template <typename T>
+__global__ void k_sample_rows(const V4<T>* __restrict__ posm, const V4<T>* __restrict__ acc,
+                              const V4<T>* __restrict__ acc_sr, const int* __restrict__ id, long long n,
+                              const int* __restrict__ ids, int m, double* __restrict__ pos_o, double* __restrict__ acc_o,
+                              double* __restrict__ sr_o) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int me = id[i];
+  int lo = 0, hi = m;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (ids[mid] < me) lo = mid + 1; else hi = mid;
+  }
+  if (lo >= m || ids[lo] != me) return;
+  if (pos_o) {
+    const V4<T> p = posm[i];
+    pos_o[3 * lo] = (double)p.x, pos_o[3 * lo + 1] = (double)p.y, pos_o[3 * lo + 2] = (double)p.z;
+  }
+  if (acc_o) {
+    const V4<T> a = acc[i];
+    acc_o[3 * lo] = (double)a.x, acc_o[3 * lo + 1] = (double)a.y, acc_o[3 * lo + 2] = (double)a.z;
+  }
+  if (sr_o) {
+    const V4<T> a = acc_sr[i];
+    sr_o[3 * lo] = (double)a.x, sr_o[3 * lo + 1] = (double)a.y, sr_o[3 * lo + 2] = (double)a.z;
+  }
+}
+
+template <typename T>
+int get_sample(p3m_ctx* c, const int32_t* ids, long long m, double* pos, double* acc, double* acc_sr) {
+  State<T>& s = Sel<T>::st(c);
+  if (m == 0) return 0;
+  int* d_ids = nullptr;
+  double* d_out = nullptr;
+  P3M_CUDA(cudaMallocAsync((void**)&d_ids, sizeof(int) * (size_t)m, c->stream));
+  P3M_CUDA(cudaMallocAsync((void**)&d_out, sizeof(double) * 9 * (size_t)m, c->stream));
+  P3M_CUDA(cudaMemcpyAsync(d_ids, ids, sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, c->stream));
+  P3M_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * 9 * (size_t)m, c->stream));
+  if (c->n > 0) {
+    k_sample_rows<T><<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(
+        s.posm, s.acc, s.acc_sr, s.id, c->n, d_ids, (int)m, pos ? d_out : nullptr, acc ? d_out + 3 * m : nullptr,
+        acc_sr ? d_out + 6 * m : nullptr);
+    P3M_LAUNCH_CHECK(c);
+  }
+  if (pos) P3M_CUDA(cudaMemcpyAsync(pos, d_out, sizeof(double) * 3 * (size_t)m, cudaMemcpyDeviceToHost, c->stream));
+  if (acc) P3M_CUDA(cudaMemcpyAsync(acc, d_out + 3 * m, sizeof(double) * 3 * (size_t)m, cudaMemcpyDeviceToHost, c->stream));
+  if (acc_sr) P3M_CUDA(cudaMemcpyAsync(acc_sr, d_out + 6 * m, sizeof(double) * 3 * (size_t)m, cudaMemcpyDeviceToHost, c->stream));
+  P3M_CUDA(cudaFreeAsync(d_ids, c->stream));
+  P3M_CUDA(cudaFreeAsync(d_out, c->stream));
+  P3M_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 template <typename T>
 int escaped_now(p3m_ctx* c, int* escaped) {
   State<T>& s = Sel<T>::st(c);
@@ -263,6 +321,8 @@ template int diagnostics<float>(p3m_ctx*, double*);
 template int diagnostics<double>(p3m_ctx*, double*);
 template int get_acc_parts<float>(p3m_ctx*, double*, double*);
 template int get_acc_parts<double>(p3m_ctx*, double*, double*);
+template int get_sample<float>(p3m_ctx*, const int32_t*, long long, double*, double*, double*);
+template int get_sample<double>(p3m_ctx*, const int32_t*, long long, double*, double*, double*);
 template int escaped_now<float>(p3m_ctx*, int*);
 template int escaped_now<double>(p3m_ctx*, int*);
 

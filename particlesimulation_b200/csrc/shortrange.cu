@@ -34,6 +34,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <cmath>
+#include <type_traits>
 #include <vector>
 
 #include "ctx.cuh"
@@ -89,6 +90,13 @@ struct TableRef<float, COPIES> {
     base = 0;
   }
   __device__ __forceinline__ void finish(volatile unsigned* slots) { base = slots[threadIdx.x & 31]; }
+  // `bits` = fma.rz(u, 499, 2^23) reinterpreted: index in the low mantissa bits, exponent folded into `base`
+  __device__ __forceinline__ V2<float> at(unsigned bits) const {
+    const unsigned addr = base + (bits << kShift);
+    V2<float> e;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(e.x), "=f"(e.y) : "r"(addr));
+    return e;
+  }
   __device__ __forceinline__ V2<float> get(float u) const {  // 0 <= u <= 1
     const unsigned addr =
         base + ((unsigned)__float_as_int(__fmaf_rz(u, float(kSRTable - 1), 8388608.0f)) << kShift);
@@ -212,9 +220,10 @@ struct PPCfg {
 // of its own targets, stages each surviving box in its private shared-memory slice (next box prefetched
 // into registers meanwhile) and runs the inner loop with broadcast LDS.128.  No block-wide barrier in
 // the loop: the warps of a CTA only share the replicated force table.
-// Staged coordinates are (p - origin) / re with origin = a multiple of 4 below the 27-cell neighbourhood:
-// the subtraction is exact in fp32 (same binade grid, result < 16), the one rounding of the scaling is
-// 2^-24 relative to a number <= 11 / re.
+// Staged coordinates are (p - origin) / re with origin = the centre of the target cell: |p - origin| <= 1.5
+// cells, so the subtraction of two nearby fp32 numbers is exact or within half an ulp of the POSITION (the
+// granularity the reference's own x_i - x_j works on) and the one rounding of the scaling is 2^-24 relative to
+// a number <= 1.5 hc / re ~ 1.6 -- about 1e-7 of the cutoff on every staged coordinate.
 template <typename T, bool TABLE, bool COUNT, bool UNIMASS, int SUB>
 __global__ void __launch_bounds__(PPCfg<T>::kWarps * 32, PPCfg<T>::kCtasPerSm)
 k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
@@ -269,9 +278,9 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
     }
     const int cx = (int)compact3(q), cy = (int)compact3(q >> 1), cz = (int)compact3(q >> 2);
     // staging frame of this item
-    const T ox = TABLE ? floor(T(cx - 1) * g.hcx * T(0.25)) * T(4) : T(0);
-    const T oy = TABLE ? floor(T(cy - 1) * g.hcy * T(0.25)) * T(4) : T(0);
-    const T oz = TABLE ? floor(T(cz - 1) * g.hcz * T(0.25)) * T(4) : T(0);
+    const T ox = TABLE ? (T(cx) + T(0.5)) * g.hcx : T(0);
+    const T oy = TABLE ? (T(cy) + T(0.5)) * g.hcy : T(0);
+    const T oz = TABLE ? (T(cz) + T(0.5)) * g.hcz : T(0);
     p0.x = (p0.x - ox) * scl, p0.y = (p0.y - oy) * scl, p0.z = (p0.z - oz) * scl;
     p1.x = (p1.x - ox) * scl, p1.y = (p1.y - oy) * scl, p1.z = (p1.z - oz) * scl;
     auto stage = [&](V4<T> v) { return V4<T>{(v.x - ox) * scl, (v.y - oy) * scl, (v.z - oz) * scl, v.w}; };
@@ -358,6 +367,232 @@ k_pp_tiled(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
   if (COUNT) {
     atomicAdd(&pair_counts[0], checked);
     atomicAdd(&pair_counts[1], inrange);
+  }
+}
+
+// ---- packed-FP32 dense-cell kernel (fp32, tabulated force, equal masses: the reference's default set-up) ------
+// Same work decomposition as k_pp_tiled (autonomous warps, 64-target items, exact box culling, private staging
+// slice, register prefetch), but the pair body runs on sm_100's two-wide FP32 instructions
+// (add / mul / fma .f32x2 -> SASS FADD2 / FMUL2 / FFMA2): one lane processes 2 targets x 2 sources per
+// iteration, the two SOURCES of a pair sharing each packed instruction.  The scalar body costs 13 issue slots
+// per pair and the kernel was issue-bound (ncu r01: issue-active 86 %, FMA pipe 64 %); packed, a pair costs
+//   3 FADD2 + FMUL2 + FFMA2 + 2 FFMA.SAT (f32x2 has no .sat) + FFMA2.RZ + 2 LEA + 2 LDS.64 + 2 FFMA + 3 FFMA2
+//   = 17 slots per TWO pairs, plus 2 broadcast LDS per FOUR pairs = 9 slots per pair,
+// which moves the bound from the issue port to the FMA pipe itself (11 lane-cycles per pair either way).
+// Sources are staged NEGATED and interleaved pairwise, (-xa,-xb,-ya,-yb) | (-za,-zb), so that d = p + (-s) is
+// one FADD2 per axis with the target coordinate duplicated in a register pair.  Arithmetic per pair is the
+// scalar kernel's, operation for operation (same roundings); only the summation order differs (even and odd
+// sources of a box are summed separately and added at the end), which stays fixed run to run.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2_rz(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+// measured on B200 (C2, ms per short-range phase): 16 warps x 2 CTAs / unroll 4 (64 registers): 111.1;
+// 16 x 2 / 8: 110.0; 12 x 2 / 4 (80 registers): 104.9; 12 x 2 / 8: 102.8; 8 x 2 / 8 (126 registers): 101.8 --
+// instruction-level parallelism inside a warp pays more than resident warps.
+#ifndef P3M_PK_WARPS
+#define P3M_PK_WARPS 8
+#endif
+#ifndef P3M_PK_UNROLL
+#define P3M_PK_UNROLL 8
+#endif
+#ifndef P3M_PK_CTAS
+#define P3M_PK_CTAS 2
+#endif
+struct PackedCfg {
+  static constexpr int kCopies = 16;
+  static constexpr int kWarps = P3M_PK_WARPS;
+  static constexpr int kUnroll = P3M_PK_UNROLL;      // source PAIRS per unrolled inner-loop body
+  static constexpr int kCtasPerSm = P3M_PK_CTAS;
+  static constexpr int kSub = 32;                    // sources per box (== kPPSub)
+  static constexpr int kSliceBytes = kSub * 12;      // per warp: 16 x (xa,xb,ya,yb) + 16 x (za,zb)
+  static constexpr size_t smem() { return sizeof(float) * 2 * kSRTable * kCopies + (size_t)kSliceBytes * kWarps + 128; }
+};
+
+// one target against one packed source pair; (ax, ay, az) hold the two partial sums side by side
+__device__ __forceinline__ void pair2_acc(f32x2 px, f32x2 py, f32x2 pz, f32x2 nsx, f32x2 nsy, f32x2 nsz,
+                                          const TableRef<float, PackedCfg::kCopies>& tab, f32x2 k499, f32x2 kbias,
+                                          f32x2& ax, f32x2& ay, f32x2& az) {
+  const f32x2 dx = add2(px, nsx), dy = add2(py, nsy), dz = add2(pz, nsz);
+  const f32x2 t = fma2(dy, dy, mul2(dx, dx));
+  float ta, tb, dza, dzb;
+  unpack2(t, ta, tb);
+  unpack2(dz, dza, dzb);
+  const float ua = fma_sat<float>(dza, dza, ta), ub = fma_sat<float>(dzb, dzb, tb);
+  const f32x2 u = pack2(ua, ub);
+  const f32x2 idx = fma2_rz(u, k499, kbias);  // floor(499 u) in the low mantissa bits of each half
+  float ia, ib;
+  unpack2(idx, ia, ib);
+  const V2<float> ea = tab.at((unsigned)__float_as_int(ia)), eb = tab.at((unsigned)__float_as_int(ib));
+  const float fa = fmaf(ea.y, ua, ea.x), fb = fmaf(eb.y, ub, eb.x);
+  const f32x2 f = pack2(fa, fb);
+  ax = fma2(f, dx, ax), ay = fma2(f, dy, ay), az = fma2(f, dz, az);
+}
+
+__global__ void __launch_bounds__(PackedCfg::kWarps * 32, PackedCfg::kCtasPerSm)
+k_pp_packed(const V4<float>* __restrict__ posm, const int* __restrict__ cell_start,
+            const V4<float>* __restrict__ aabb, const V4<float>* __restrict__ gposm,
+            const int* __restrict__ gcell_start, const V4<float>* __restrict__ gaabb,
+            const int* __restrict__ items, const unsigned* __restrict__ order, int* __restrict__ counters,
+            Geom<float> g, SRParams<float> sp, const float* __restrict__ g_tab, float uni_mass,
+            V4<float>* __restrict__ acc, V4<float>* __restrict__ acc_sr) {
+  using T = float;
+  constexpr int COPIES = PackedCfg::kCopies, SUB = PackedCfg::kSub;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  V2<T>* s_tab = reinterpret_cast<V2<T>*>(smem_raw);
+  unsigned char* s_slices = smem_raw + sizeof(V2<T>) * kSRTable * COPIES;
+  volatile unsigned* s_tb = reinterpret_cast<volatile unsigned*>(s_slices + PackedCfg::kSliceBytes * PackedCfg::kWarps);
+  const T re = sqrt(sp.re2);
+  const T scl = T(1) / re;
+  load_table<T, COPIES>(g_tab, s_tab, re * uni_mass);
+  TableRef<T, COPIES> tref(s_tab, s_tb);
+  __syncthreads();
+  tref.finish(s_tb);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float4* s_xy = reinterpret_cast<float4*>(s_slices + wid * PackedCfg::kSliceBytes);       // 16 x (-xa,-xb,-ya,-yb)
+  float2* s_z = reinterpret_cast<float2*>(s_slices + wid * PackedCfg::kSliceBytes + 256);  // 16 x (-za,-zb)
+  float* s_xy_w = reinterpret_cast<float*>(s_xy) + (lane >> 1) * 4 + (lane & 1);
+  float* s_z_w = reinterpret_cast<float*>(s_z) + lane;
+  const int nitems = counters[0];
+  const T cut2 = sp.re2 * (T(1) + T(1e-5));
+  const f32x2 k499 = pack2(float(kSRTable - 1), float(kSRTable - 1)), kbias = pack2(8388608.0f, 8388608.0f);
+  for (;;) {
+    int it = 0;
+    if (lane == 0) it = atomicAdd(&counters[1], 1);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    if (it >= nitems) break;
+    const int item = (int)order[it];
+    const uint32_t q = (uint32_t)items[2 * item];
+    const int t0 = items[2 * item + 1];
+    const int tend = min(cell_start[q + 1], t0 + kPPTargets);
+    const int i0 = t0 + lane, i1 = i0 + 32;
+    const bool v0 = i0 < tend, v1 = i1 < tend;
+    V4<T> p0 = posm[v0 ? i0 : t0], p1 = posm[v1 ? i1 : t0];
+    T wlo[3], whi[3];
+    {
+      T lx = min(p0.x, p1.x), ly = min(p0.y, p1.y), lz = min(p0.z, p1.z);
+      T hx = max(p0.x, p1.x), hy = max(p0.y, p1.y), hz = max(p0.z, p1.z);
+      for (int o = 16; o > 0; o >>= 1) {
+        lx = min(lx, __shfl_xor_sync(0xffffffffu, lx, o)), ly = min(ly, __shfl_xor_sync(0xffffffffu, ly, o));
+        lz = min(lz, __shfl_xor_sync(0xffffffffu, lz, o)), hx = max(hx, __shfl_xor_sync(0xffffffffu, hx, o));
+        hy = max(hy, __shfl_xor_sync(0xffffffffu, hy, o)), hz = max(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+      }
+      wlo[0] = lx, wlo[1] = ly, wlo[2] = lz, whi[0] = hx, whi[1] = hy, whi[2] = hz;
+    }
+    const int cx = (int)compact3(q), cy = (int)compact3(q >> 1), cz = (int)compact3(q >> 2);
+    // staging frame of this item (see k_pp_tiled): centre of the target cell
+    const T ox = (T(cx) + T(0.5)) * g.hcx;
+    const T oy = (T(cy) + T(0.5)) * g.hcy;
+    const T oz = (T(cz) + T(0.5)) * g.hcz;
+    const f32x2 p0x = pack2((p0.x - ox) * scl, (p0.x - ox) * scl), p0y = pack2((p0.y - oy) * scl, (p0.y - oy) * scl),
+                p0z = pack2((p0.z - oz) * scl, (p0.z - oz) * scl);
+    const f32x2 p1x = pack2((p1.x - ox) * scl, (p1.x - ox) * scl), p1y = pack2((p1.y - oy) * scl, (p1.y - oy) * scl),
+                p1z = pack2((p1.z - oz) * scl, (p1.z - oz) * scl);
+    // negated staged source; padding lanes sit beyond the cutoff of every target (u saturates, F_499 = 0)
+    auto stage_neg = [&](V4<T> v) { return V4<T>{-((v.x - ox) * scl), -((v.y - oy) * scl), -((v.z - oz) * scl), 0}; };
+    const V4<T> far_{T(64), T(64), T(64), T(0)};
+    f32x2 a0x = 0, a0y = 0, a0z = 0, a1x = 0, a1y = 0, a1z = 0;
+    for (int dz = -1; dz <= 1; ++dz)
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int x = cx + dx, y = cy + dy, z = cz + dz;
+          if (x < 0 || y < 0 || z < 0 || x >= g.mx || y >= g.my || z >= g.mz) continue;
+          const uint32_t qn = morton3((uint32_t)x, (uint32_t)y, (uint32_t)z);
+          const bool own = g.nranks == 1 || layer_owner(g, z) == g.rank;
+          const V4<T>* __restrict__ spos = own ? posm : gposm;
+          const int* __restrict__ scs = own ? cell_start : gcell_start;
+          const V4<T>* __restrict__ sbb = own ? aabb : gaabb;
+          const int s = scs[qn], e = scs[qn + 1];
+          if (s >= e) continue;
+          const int box_first = s / SUB, box_last = (e - 1) / SUB;
+          for (int b0 = box_first; b0 <= box_last; b0 += 32) {
+            const int mybox = b0 + lane;
+            bool near_ = false;
+            if (mybox <= box_last) {
+              const V4<T> blo = sbb[2 * mybox], bhi = sbb[2 * mybox + 1];
+              const T gx = max(T(0), max(blo.x - whi[0], wlo[0] - bhi.x));
+              const T gy = max(T(0), max(blo.y - whi[1], wlo[1] - bhi.y));
+              const T gz = max(T(0), max(blo.z - whi[2], wlo[2] - bhi.z));
+              near_ = gx * gx + gy * gy + gz * gz <= cut2;
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, near_);
+            if (todo == 0u) continue;
+            int k = __ffs(todo) - 1;
+            todo &= todo - 1;
+            int jb = max(s, (b0 + k) * SUB), je = min(e, (b0 + k + 1) * SUB);
+            V4<T> n0 = (jb + lane < je) ? stage_neg(spos[jb + lane]) : far_;
+            for (;;) {
+              const int npair = (je - jb + 1) >> 1;
+              __syncwarp();
+              s_xy_w[0] = n0.x, s_xy_w[2] = n0.y, *s_z_w = n0.z;
+              __syncwarp();
+              const bool more = todo != 0u;
+              if (more) {
+                k = __ffs(todo) - 1;
+                todo &= todo - 1;
+                jb = max(s, (b0 + k) * SUB), je = min(e, (b0 + k + 1) * SUB);
+                n0 = (jb + lane < je) ? stage_neg(spos[jb + lane]) : far_;
+              }
+#pragma unroll PackedCfg::kUnroll
+              for (int j = 0; j < npair; ++j) {
+                const float4 sxy = s_xy[j];
+                const float2 sz = s_z[j];
+                const f32x2 nsx = pack2(sxy.x, sxy.y), nsy = pack2(sxy.z, sxy.w), nsz = pack2(sz.x, sz.y);
+                pair2_acc(p0x, p0y, p0z, nsx, nsy, nsz, tref, k499, kbias, a0x, a0y, a0z);
+                pair2_acc(p1x, p1y, p1z, nsx, nsy, nsz, tref, k499, kbias, a1x, a1y, a1z);
+              }
+              if (!more) break;
+            }
+          }
+        }
+    // the two half sums are the sums over the even and the odd sources of every staged box
+    float lo, hi;
+    if (v0) {
+      V4<T> r;
+      unpack2(a0x, lo, hi), r.x = lo + hi;
+      unpack2(a0y, lo, hi), r.y = lo + hi;
+      unpack2(a0z, lo, hi), r.z = lo + hi;
+      r.w = 0;
+      acc_sr[i0] = r;
+      const V4<T> a = acc[i0];
+      acc[i0] = V4<T>{a.x + r.x, a.y + r.y, a.z + r.z, 0};  // correctAccelerations :55
+    }
+    if (v1) {
+      V4<T> r;
+      unpack2(a1x, lo, hi), r.x = lo + hi;
+      unpack2(a1y, lo, hi), r.y = lo + hi;
+      unpack2(a1z, lo, hi), r.z = lo + hi;
+      r.w = 0;
+      acc_sr[i1] = r;
+      const V4<T> a = acc[i1];
+      acc[i1] = V4<T>{a.x + r.x, a.y + r.y, a.z + r.z, 0};
+    }
   }
 }
 
@@ -514,13 +749,28 @@ static int run_pp(p3m_ctx* c) {
   P3M_CUDA(cub::DeviceRadixSort::SortPairsDescending(s.cub_tmp, tmp, cost, cost_sorted, idx, order,
                                                      (int)max_items, 0, 32, c->stream));
   c->launches += 5;
-  auto kern = k_pp_tiled<T, TABLE, COUNT, UNIMASS, kPPSub>;
-  const size_t smem = PPCfg<T>::smem(kPPSub);
-  P3M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<c->num_sms * PPCfg<T>::kCtasPerSm, PPCfg<T>::kWarps * 32, smem, c->stream>>>(
-      s.posm, s.cell_start, s.aabb, s.gposm, s.gcell_start, s.gaabb, s.pp_items, order, s.pp_counters, g, sp,
-      s.sr_table, (T)c->uniform_mass_code, s.acc, s.acc_sr, s.pair_counts);
-  P3M_LAUNCH_CHECK(c);
+  bool packed = false;
+  if constexpr (std::is_same<T, float>::value && TABLE && UNIMASS && !COUNT && kPPSub == PackedCfg::kSub) {
+    packed = !c->tune.scalar_pp;
+    if (packed) {
+      const size_t smem = PackedCfg::smem();
+      P3M_CUDA(cudaFuncSetAttribute(k_pp_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_pp_packed<<<c->num_sms * PackedCfg::kCtasPerSm, PackedCfg::kWarps * 32, smem, c->stream>>>(
+          s.posm, s.cell_start, s.aabb, s.gposm, s.gcell_start, s.gaabb, s.pp_items, order, s.pp_counters, g, sp,
+          s.sr_table, (float)c->uniform_mass_code, s.acc, s.acc_sr);
+      P3M_LAUNCH_CHECK(c);
+    }
+  }
+  if (!COUNT) c->packed_pp = packed;
+  if (!packed) {
+    auto kern = k_pp_tiled<T, TABLE, COUNT, UNIMASS, kPPSub>;
+    const size_t smem = PPCfg<T>::smem(kPPSub);
+    P3M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<c->num_sms * PPCfg<T>::kCtasPerSm, PPCfg<T>::kWarps * 32, smem, c->stream>>>(
+        s.posm, s.cell_start, s.aabb, s.gposm, s.gcell_start, s.gaabb, s.pp_items, order, s.pp_counters, g, sp,
+        s.sr_table, (T)c->uniform_mass_code, s.acc, s.acc_sr, s.pair_counts);
+    P3M_LAUNCH_CHECK(c);
+  }
   k_pp_sparse<T, TABLE, COUNT><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(
       s.posm, n, s.cell_start, s.gposm, s.gcell_start, g, sp, s.sr_table, s.acc, s.acc_sr, s.pair_counts);
   P3M_LAUNCH_CHECK(c);

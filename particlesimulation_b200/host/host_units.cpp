@@ -197,11 +197,11 @@ static int runGpu(const Input& in) {
   auto& after = pm.getParticles();
   putv("pm_acc", after, &Particle::acceleration);
   putv("pm_pos", after, &Particle::position);
-  std::vector<Particle> orig = after;
-  stateToOriginalUnits(orig, in.H, in.DT);
-  massToOriginalUnits(orig, in.H, in.DT, in.G);
+  // back to original units IN PLACE, as the run loops do before the diagnostics (source/pmMethod.cpp:94-105)
+  stateToOriginalUnits(after, in.H, in.DT);
+  massToOriginalUnits(after, in.H, in.DT, in.G);
   Vec3 ext = pm.totalExternalForceOrigUnits();
-  std::vector<float> misc = {SimInfo::potentialEnergy(g, orig, pm.getExternalPotential(), in.H, in.DT, in.G), ext.x, ext.y, ext.z,
+  std::vector<float> misc = {SimInfo::potentialEnergy(g, after, pm.getExternalPotential(), in.H, in.DT, in.G), ext.x, ext.y, ext.z,
                              pm.escapedComputationalBox() ? 1.0f : 0.0f, pm.getH(), pm.getDT(), pm.getG()};
   // (2) CUDA-build spelling: mesh size instead of a Grid, explicit copies, vector getters
   PMMethodGPU gpu(in.state, in.masses, box, field, pot, in.H, in.DT, in.G, InterpolationScheme::TSC,

@@ -28,9 +28,15 @@ void check(int rc, const char* what) {
 struct PMMethod::Impl {
   p3m_params prm{};
   p3m_ctx* ctx = nullptr;
-  std::vector<Particle> particles;  // host mirror, in `hostUnitsCode ? code : original` units
-  std::vector<float> massOriginal;  // never changes
-  bool hostUnitsCode = false;       // the reference's vector is in original units until run() converts it
+  // Host mirror of the reference's `particles` member.  Like the reference's vector its units are the CALLER's
+  // business: the constructor fills it in original units, run() converts it, pmMethodStep() takes it as code
+  // units (source/pmMethod.cpp:137-144 runs on whatever the vector holds; P3MMethod::run converts it through
+  // getParticles() first, source/p3mMethod.cpp:73-74).  Whenever the device state is copied back the mirror is
+  // in code units (positions, velocities, masses), which is what the reference's vector holds after the same
+  // calls; `hostUnitsCode` only records that so that download() and run() know.
+  std::vector<Particle> particles;
+  std::vector<float> massOriginal;  // masses in original units (constructor / head of run())
+  bool hostUnitsCode = false;
   bool hostIsNewer = true;          // host vector must be uploaded before the next device call
   bool deviceIsNewer = false;       // device state must be downloaded before host code reads the vector
   Grid* grid = nullptr;
@@ -54,7 +60,8 @@ struct PMMethod::Impl {
     ctx = nullptr;
     hostIsNewer = true;
   }
-  void upload() {
+  // `units`: how the operation that needs the particles on the device interprets the mirror
+  void upload(int units) {
     ensureCtx();
     if (!hostIsNewer) return;
     const size_t n = particles.size();
@@ -64,14 +71,16 @@ struct PMMethod::Impl {
       const Particle& p = particles[i];
       pos[3 * i] = p.position.x, pos[3 * i + 1] = p.position.y, pos[3 * i + 2] = p.position.z;
       vel[3 * i] = p.velocity.x, vel[3 * i + 1] = p.velocity.y, vel[3 * i + 2] = p.velocity.z;
-      // masses always come from the constructor's vector (the host mirror's p.mass follows the units of the
-      // mirror); converted with the reference's own fp32 expression (include/unitConversions.h:42-44)
-      mass[i] = hostUnitsCode ? massToCodeUnits(massOriginal[i], prm.H, prm.DT, prm.G) : massOriginal[i];
+      mass[i] = p.mass;  // same units as the positions: the mirror is converted as a whole
     }
-    check(p3m_set_particles(ctx, pos, vel, mass, (int64_t)n, hostUnitsCode ? P3M_UNITS_CODE : P3M_UNITS_ORIGINAL),
-          "p3m_set_particles");
+    check(p3m_set_particles(ctx, pos, vel, mass, (int64_t)n, units), "p3m_set_particles");
     hostIsNewer = false;
     deviceIsNewer = false;
+    hostUnitsCode = true;  // from here on the device state (code units) is what download() mirrors
+    if (units == P3M_UNITS_CODE)
+      for (size_t i = 0; i < n; ++i) massOriginal[i] = massToOriginalUnits(particles[i].mass, prm.H, prm.DT, prm.G);
+    else
+      for (size_t i = 0; i < n; ++i) massOriginal[i] = particles[i].mass;
   }
   // host vector <- device, in the units the reference's vector would be in at this point
   void download() {
@@ -88,13 +97,8 @@ struct PMMethod::Impl {
       p.acceleration = Vec3{acc[3 * i], acc[3 * i + 1], acc[3 * i + 2]};  // always code units in the reference
       p.integerStepVelocity = p.velocity + 0.5f * p.acceleration;         // source/leapfrog.cpp:10-14, code units
       p.mass = massToCodeUnits(massOriginal[i], H, DT, prm.G);
-      if (!hostUnitsCode) {
-        p.position = positionToOriginalUnits(p.position, H);
-        p.velocity = velocityToOriginalUnits(p.velocity, H, DT);
-        p.integerStepVelocity = velocityToOriginalUnits(p.integerStepVelocity, H, DT);
-        p.mass = massOriginal[i];
-      }
     }
+    (void)H, (void)DT;
     deviceIsNewer = false;
   }
   void hostCallbackField(const std::function<Vec3(Vec3)>& field) {
@@ -195,9 +199,11 @@ std::vector<Particle>& PMMethod::getParticles() {
 }
 
 void PMMethod::copyParticlesDeviceToHost() { impl->download(); }
+// include_gpu/PMMethodGPU.h:46-47; the reference calls it with the vector already in code units
+// (source/p3mMethod.cpp:77-79,138-140)
 void PMMethod::copyParticlesHostToDevice() {
   impl->hostIsNewer = true;
-  impl->upload();
+  impl->upload(P3M_UNITS_CODE);
 }
 
 void PMMethod::initGreensFunction() {
@@ -208,7 +214,7 @@ void PMMethod::initGreensFunction() {
 // source/pmMethod.cpp:137-144.  Like the reference it works on the particles as they are (code units
 // once run() has converted them); after the call the accelerations live on the device.
 void PMMethod::pmMethodStep() {
-  impl->upload();
+  impl->upload(P3M_UNITS_CODE);
   check(p3m_bin_sort(impl->ctx), "p3m_bin_sort");
   check(p3m_deposit(impl->ctx), "p3m_deposit");
   check(p3m_poisson(impl->ctx), "p3m_poisson");
@@ -217,28 +223,28 @@ void PMMethod::pmMethodStep() {
   impl->deviceIsNewer = true;
 }
 
+// source/pmMethod.cpp:146-156: the positions AS THEY ARE in the vector against the box (the run loops call it
+// right after stateToOriginalUnits)
 bool PMMethod::escapedComputationalBox() {
-  impl->upload();
-  int e = 0;
-  check(p3m_escaped(impl->ctx, &e), "p3m_escaped");
-  return e != 0;
+  impl->download();
+  const float bx = impl->prm.box[0], by = impl->prm.box[1], bz = impl->prm.box[2];
+  for (const Particle& p : impl->particles) {
+    const Vec3& x = p.position;
+    if (!(x.x >= 0 && x.x <= bx && x.y >= 0 && x.y <= by && x.z >= 0 && x.z <= bz)) return true;
+  }
+  return false;
 }
 
+// source/pmMethod.cpp:158-162: sum of p.mass * externalField(p.position) over the vector AS IT IS (the run loops
+// call it with positions and masses back in original units)
 Vec3 PMMethod::totalExternalForceOrigUnits() {
   if (impl->extIsZero) return Vec3::zero();
-  if (impl->extOnDevice) {
-    impl->upload();
-    double d[11];
-    check(p3m_diagnostics(impl->ctx, d), "p3m_diagnostics");
-    return Vec3{(float)d[8], (float)d[9], (float)d[10]};
-  }
   impl->download();
   Vec3 total = Vec3::zero();
-  for (size_t i = 0; i < impl->particles.size(); ++i) {
-    Vec3 pos = impl->particles[i].position;
-    if (impl->hostUnitsCode) pos = positionToOriginalUnits(pos, H);
-    total += impl->massOriginal[i] * externalField(pos);
-  }
+  const p3m_params& q = impl->prm;
+  const Vec3 c = Vec3::create(q.ext_center[0], q.ext_center[1], q.ext_center[2]);
+  for (const Particle& p : impl->particles)
+    total += p.mass * (externalField ? externalField(p.position) : sphRadDecrField(p.position, c, q.ext_R, q.ext_M, G));
   return total;
 }
 
@@ -282,12 +288,13 @@ void PMMethod::runLoop(StateRecorder& rec, int simLength, bool diagnostics, bool
   Impl& s = *impl;
   const size_t n = s.particles.size();
   SimInfo simInfo;
-  if (s.hostUnitsCode) throw std::runtime_error("run(): particles were already converted to code units");
+  if (s.hostUnitsCode)
+    throw std::runtime_error("run(): the particles are in code units already (run() converts them itself, "
+                             "source/pmMethod.cpp:72-73)");
   if (diagnostics) simInfo.setInitialMomentum(s.particles);  // sum m * v, original units
   if (s.prm.p3m != (p3m ? 1 : 0)) throw std::logic_error("run(): context mode mismatch");
   s.hostIsNewer = true;
-  s.upload();  // stateToCodeUnits + massToCodeUnits happen on the device
-  s.hostUnitsCode = true;
+  s.upload(P3M_UNITS_ORIGINAL);  // stateToCodeUnits + massToCodeUnits happen on the device
   const bool callback = !s.extIsZero && !s.extOnDevice;
   auto force = [&]() {
     check(p3m_force(s.ctx), "p3m_force");  // pmMethodStep [+ short range + correctAccelerations]
@@ -386,7 +393,7 @@ P3MMethod::P3MMethod(PMMethod& pm, std::tuple<float, float, float> compBoxSize, 
 
 void P3MMethod::forceStep() {
   PMMethod::Impl& s = *pmMethod.impl;
-  s.upload();
+  s.upload(P3M_UNITS_CODE);  // like pmMethodStep(): the vector is taken as code units
   check(p3m_force(s.ctx), "p3m_force");
   if (!s.extIsZero && !s.extOnDevice) s.hostCallbackField(pmMethod.externalField);
   s.deviceIsNewer = true;

@@ -126,9 +126,11 @@ def clustered_disk_halo(n, box=60.0, seed=42, halo_a=12.0, halo_rmax=27.0, disk_
     vel[:nd, 2] = v * cs
     del u, r, phi, cs, sn, menc, v
     # halo
-    u = np.maximum(rng.random(nh, dtype=f32), f32(1e-7))
-    r = f32(halo_a) / np.sqrt(u ** f32(-2.0 / 3.0) - f32(1))
-    r = np.minimum(r, f32(halo_rmax))
+    # Plummer CDF truncated at halo_rmax (u scaled to [0, F(rmax)]): no particles beyond the cut and no shell of
+    # clamped ones at it; evaluated in float64 (u^(-2/3) - 1 loses everything near u = 1 in float32)
+    frac = halo_rmax ** 3 / (halo_rmax ** 2 + halo_a ** 2) ** 1.5
+    u = np.maximum(rng.random(nh), 1e-12) * frac
+    r = np.minimum(halo_a / np.sqrt(u ** (-2.0 / 3.0) - 1.0), halo_rmax).astype(f32)
     cos_t = f32(1) - f32(2) * rng.random(nh, dtype=f32)
     sin_t = np.sqrt(np.maximum(f32(0), f32(1) - cos_t * cos_t))
     phi = f32(2 * np.pi) * rng.random(nh, dtype=f32)

@@ -68,9 +68,42 @@ def run_case(name, p, pos, vel, mass, p3m, steps):
     return out
 
 
+def run_generated(name, p, ic, p3m):
+    """Device-side initial conditions: every rank generates only its own z-slab (p3m_generate_particles); the
+    union must be the sampled set, and the force must equal the single-GPU force on the uploaded set."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    prm = to_p3m(p, p3m=p3m, zero_degenerate=True)
+    prm.device = int(os.environ.get("LOCAL_RANK", 0))
+    ctx = pdist.create_context(prm, capi)
+    ctx.generate_particles(ic)
+    n_local0 = ctx.n
+    counts = allsum(np.array([ctx.n], np.int64))
+    gp = allsum(ctx.get_particles(capi.UNITS_ORIGINAL, want=("pos",))[0])
+    ctx.green_init()
+    ctx.force()
+    acc = allsum(ctx.get_particles(capi.UNITS_CODE, want=("acc",))[2])
+    ctx.close()
+    out = {}
+    if rank == 0:
+        pos, vel, mass = capi.sample_particles(ic)
+        single = capi.Context(prm)
+        single.set_particles(pos, vel, mass)
+        single.green_init()
+        single.force()
+        acc1 = single.get_particles(capi.UNITS_CODE, want=("acc",))[2]
+        single.close()
+        out = dict(case=name, generated=1, n=int(ic.n), total=int(counts[0]), n_local0=int(n_local0),
+                   pos=rel_l2(gp, pos), acc=rel_l2(acc, acc1))
+    return out
+
+
 def main():
     pdist.init_process_group("nccl")
     results = []
+    p, _, _, _ = plummer_case(20000)
+    results.append(run_generated("generated_plummer_p3m", p, capi.ic_plummer(20000, seed=42), True))
+    p, _, _, _ = uniform_case(20000, gfunc=0)
+    results.append(run_generated("generated_uniform_pm", p, capi.ic_uniform(20000, [5.0] * 3, [55.0] * 3, seed=1), False))
     # one Plummer sphere centred ON the slab boundary (world = 2): heavy ghost traffic, migration
     p, pos, vel, mass = plummer_case(20000)
     results.append(run_case("plummer_p3m", p, pos, vel, mass, True, 5))

@@ -1,0 +1,64 @@
+"""N4: the device-side brute-force accuracy oracle (csrc/directsum.cu, p3m_direct_sum).
+
+* its short-range mode is pinned to the CPU oracle's fp64 short-range sum (tabulated and analytic law);
+* the thesis' accuracy experiment (source/demos.cpp:593-657 p3mAccuracyAssignments + script/p3m_accuracy.py:32-36):
+  P3M forces against the softening-free Newtonian direct sum, metric = mean over particles of
+  |F_p3m - F_pp| / (|F_pp| + 1e-10), on a linear disk with re = a, eps = 0, analytic short-range law."""
+import numpy as np
+import pytest
+
+import refapi
+from common import plummer_case, to_p3m
+from particlesimulation_b200 import capi
+from refapi import Oracle, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("use_table", [True, False])
+def test_direct_sum_short_range_matches_oracle(use_table):
+    p, pos, vel, mass = plummer_case(6000, use_table=use_table)
+    o = Oracle("f64")
+    pc32, _, mc32 = Oracle("f32").to_code_units(p, pos, vel, mass)
+    sr_ref = o.sr_forces(p, pc32.astype(np.float64), mc32.astype(np.float64)) / mc32[:, None].astype(np.float64)
+    with capi.Context(to_p3m(p, p3m=True)) as ctx:
+        ctx.set_particles(pos, vel, mass)
+        ids = np.arange(0, 6000, 7)
+        direct = ctx.direct_sum(pc32[ids].astype(np.float64), capi.SUM_SHORT_RANGE)
+        ctx.bin_sort()
+        ctx.short_range()
+        _, sr = ctx.acc_parts()
+    # the oracle's table holds fp32-built values (like the device table the direct sum reads in double)
+    assert rel_l2(direct, sr_ref[ids]) < 2e-6
+    assert rel_l2(sr[ids], direct) < 2e-5  # fast path vs brute force
+
+
+def mean_relative_error(f, f_ref):
+    num = np.linalg.norm(f - f_ref, axis=1)
+    return float(np.mean(num / (np.linalg.norm(f_ref, axis=1) + 1e-10)))
+
+
+def test_p3m_accuracy_against_newtonian_direct_sum():
+    n = 1 << 14
+    grid, box = (128, 128, 64), (60.0, 60.0, 30.0)
+    ic = capi.ic_disk_linear(n, center=(30.0, 30.0, 15.0), seed=42)
+    pos, vel, mass = capi.sample_particles(ic)
+    f32 = np.float32
+    H = f32(60.0) / f32(64)
+    errs = {}
+    for amul in (8, 15):
+        a = float(f32(0.2) * f32(amul) * H)
+        p = refapi.make_params(n, grid, box, gfunc=refapi.S1_OPTIMAL, diameter=a, cutoff=a, softening=0.0,
+                               use_table=False, zero_degenerate=True)
+        with capi.Context(to_p3m(p, p3m=True)) as ctx:
+            ctx.set_particles(pos, vel, mass)
+            ctx.force()
+            gpos, _, acc = ctx.get_particles(capi.UNITS_CODE)
+            pm, _ = ctx.acc_parts()
+            newton = ctx.direct_sum(gpos.astype(np.float64), capi.SUM_NEWTON, 0.0)
+        errs[amul] = (mean_relative_error(acc, newton), mean_relative_error(pm, newton))
+    # P3M with a = 3H reproduces the direct sum to better than a percent on average; the mesh alone does not
+    assert errs[15][0] < 1e-2, errs
+    assert errs[15][1] > 5 * errs[15][0], errs
+    # a wider cloud (more of the force moved to the exact short-range sum) is more accurate (thesis figure)
+    assert errs[15][0] < errs[8][0], errs

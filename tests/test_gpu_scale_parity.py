@@ -83,7 +83,17 @@ def test_c1_literal_p3m_vs_compiled_reference():
     assert np.array_equal(dims, r["dims"])
     assert np.array_equal(cc, r["cell"]), "chaining cells must be bit-exact"
     assert rel_l2(pm, r["acc_pm"]) < TOL32
-    mcode = Oracle("f32").to_code_units(p, pos, vel, mass)[2]
+    # fp64 evaluation of the same sum on the SAME fp32 code-unit positions and masses
+    pc32, _, mcode = Oracle("f32").to_code_units(p, pos, vel, mass)
+    mc64 = mcode.astype(np.float64)
+    sr64 = Oracle("f64").sr_forces(p, pc32.astype(np.float64), mc64)
+    ours, theirs = rel_l2(sr * mc64[:, None], sr64), rel_l2(r["sr_force"], sr64)
+    print(f"short-range force vs fp64: ours {ours:.2e}, reference {theirs:.2e}; ours vs reference "
+          f"{rel_l2(sr * mcode[:, None].astype(np.float64), r['sr_force']):.2e}")
+    # a thin disk: the short-range sums cancel to a small net force, and BOTH fp32 evaluations sit ~1.5e-4 from
+    # the fp64 one (fp32 rounding of r^2 / delta^2 picks the neighbouring table bucket now and then); ours is no
+    # further from it than the reference is, and the two agree within north_star's tolerance
+    assert ours < 1.2 * theirs + 1e-6
     assert rel_l2(sr * mcode[:, None].astype(np.float64), r["sr_force"]) < TOL32
     assert rel_l2(acc, r["acc"]) < TOL32
 

@@ -257,6 +257,7 @@ def test_reference_tree_demo_runs_galaxy_p3m_like_the_reference(tmp_path):
     128 x 128 x 64, TSC, S1-optimal, P3M, bulge field through the std::function callback, 200 steps) runs on
     the GPU; its first diagnostic rows follow the UNMODIFIED reference's CPU run of the same demo."""
     out = tmp_path / "rt"
+    out.mkdir()  # the reference's StateRecorder does not create its output directory
     r = subprocess.run([REFTREE, str(out)], capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     diag = np.concatenate([np.loadtxt(out / f, ndmin=2) for f in
