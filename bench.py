@@ -190,34 +190,42 @@ def c2_ic(capi, n):
 
 C5_GRIDS = {1: (256, 256, 256), 2: (256, 256, 512), 4: (512, 512, 256), 8: (512, 512, 512)}
 N_C5_PER_GPU = 1 << 23
+VEL_SIGMA_CELLS = 0.05   # velocity dispersion of the uniform sets, mesh cells per step
 
 
-def c5_setup(capi, world, n_per_gpu=N_C5_PER_GPU, timing=True, device=None):
+def uniform_margin_cells(args):
+    """Uniform sets drift freely (their self-gravity is negligible over a bench run): keep every particle
+    inside the box for all the steps one context executes (warm-up + timed + end-to-end), 6 sigma."""
+    total = args.warmup + 2 * max(args.steps, 10) + 4
+    return max(4.0, 6 * VEL_SIGMA_CELLS * total)
+
+
+def c5_setup(capi, world, n_per_gpu=N_C5_PER_GPU, timing=True, device=None, margin=8.0):
     """BASELINE.json configs[4]: P3M weak-scaling sweep, 2^23 particles per GPU, meshes 256^3 / 256^2 x 512 /
     512^2 x 256 / 512^3 (0.5 particles per mesh cell throughout), ONE global distribution: a
-    uniform cube filling the occupied half of the mesh per axis (4 particles per occupied cell, ~155 partners
-    inside the cutoff), with a velocity dispersion of 0.3 cells per step, so that every slab boundary is
-    crossed by migrating particles and lined with ghost layers."""
+    uniform cube filling the occupied half of the mesh per axis (~4 particles per occupied cell, ~160 partners
+    inside the cutoff), with a small velocity dispersion, so that every slab boundary is crossed by migrating
+    particles and lined with ghost layers.  `margin` (cells) keeps the drifting set inside the box."""
     grid = C5_GRIDS[world]
     box = tuple(H_C2 * (g // 2) for g in grid)
     prm = p3m_params(capi, grid, box, timing, device=device)
     n = n_per_gpu * world
-    lo = [2 * H_C2] * 3
-    hi = [b - 2 * H_C2 for b in box]
-    ic = capi.ic_uniform(n, lo, hi, total_mass=float(world), vel_sigma=0.3 * H_C2, seed=42)
+    lo = [margin * H_C2] * 3
+    hi = [b - margin * H_C2 for b in box]
+    ic = capi.ic_uniform(n, lo, hi, total_mass=float(world), vel_sigma=VEL_SIGMA_CELLS * H_C2, seed=42)
     return prm, ic, grid
 
 
-def c3_setup(capi, n=1 << 24, grid=512, timing=True, device=None):
+def c3_setup(capi, n=1 << 24, grid=512, timing=True, device=None, margin=8.0):
     """BASELINE.json configs[2]: PM uniform cube, 2^24 particles, 512^3 mesh, TSC, discrete Laplacian."""
     box = (60.0, 60.0, 60.0)
     prm = p3m_params(capi, (grid,) * 3, box, timing, p3m=0, gfunc=capi.DISCRETE_LAPLACIAN, device=device)
     H = float(prm.H)
-    ic = capi.ic_uniform(n, [2 * H] * 3, [60.0 - 2 * H] * 3, total_mass=1.0, vel_sigma=0.3 * H, seed=42)
+    ic = capi.ic_uniform(n, [margin * H] * 3, [60.0 - margin * H] * 3, total_mass=1.0, vel_sigma=VEL_SIGMA_CELLS * H, seed=42)
     return prm, ic
 
 
-def c4_setup(capi, n=1 << 26, grid=1024, timing=True, device=None):
+def c4_setup(capi, n=1 << 26, grid=1024, timing=True, device=None, margin=None):
     """BASELINE.json configs[3]: P3M clustered disk + halo, 2^26 particles, 1024^3 mesh; the softening of C2 in
     mesh units."""
     box = BOX_C2
@@ -416,6 +424,9 @@ def run_single(args, capi, cu, prm, ic, label, flush, flush_bytes, want_e2e=True
     t_wall0 = time.time()
     ms = timed_window(cu, ctx, args.steps, flush, flush_bytes, clocks)
     t_wall = time.time() - t_wall0
+    if ctx.escaped():
+        raise RuntimeError(f"{label}: a particle left the computational box during the timed steps (the run loop would "
+                           "have stopped, source/pmMethod.cpp:108-111): the measurement is void")
     phases = {k: v / args.steps for k, v in ctx.phase_ms(reset=True).items()}
     launches = ctx.launches - launches0
     out = {"ctx": ctx, "n": n, "ms": ms, "phases": phases, "launches": launches, "wall": t_wall, "label": label}
@@ -507,14 +518,17 @@ def run_ours(args):
     _, sr = ctx.acc_parts()
     ids = parity_sample_ids(n)
     mcode = np.full(n, mass_code(ctx.params, np.float32(1.0) / np.float32(n)), np.float64)
-    t0 = time.time()
-    sr_host = sr_direct_host(capi, ctx, gpos, mcode, ids)
-    host_s = time.time() - t0
     sr_dev = ctx.direct_sum(gpos[ids].astype(np.float64), capi.SUM_SHORT_RANGE)
-    parity = {"sample": len(ids), "sr_rel_l2": rel_l2(sr[ids], sr_host), "sr_rel_l2_vs_device_direct_sum": rel_l2(sr[ids], sr_dev),
-              "direct_sum_vs_host_rel_l2": rel_l2(sr_dev, sr_host), "tolerance": 1e-4, "host_fp64_seconds": round(host_s, 1),
-              "what": "short-range acceleration after the timed steps, sample of particles vs (a) host fp64 evaluation of "
-                      "source/p3mMethod.cpp:240-245 over all particles, (b) p3m_direct_sum (device fp64 brute force)"}
+    hsub = np.arange(0, len(ids), 8)  # the host evaluation costs ~20 ms per particle: every 8th of the sample
+    t0 = time.time()
+    sr_host = sr_direct_host(capi, ctx, gpos, mcode, ids[hsub])
+    host_s = time.time() - t0
+    parity = {"sample": len(ids), "sr_rel_l2": rel_l2(sr[ids], sr_dev), "tolerance": 1e-4,
+              "host_sample": len(hsub), "sr_rel_l2_vs_host_fp64": rel_l2(sr[ids[hsub]], sr_host),
+              "device_direct_sum_vs_host_fp64_rel_l2": rel_l2(sr_dev[hsub], sr_host), "host_fp64_seconds": round(host_s, 1),
+              "what": "short-range acceleration after the timed steps: 4096 sampled particles vs p3m_direct_sum (device fp64 "
+                      "brute force over all particles, no cells / sort / culling); every 8th of them also vs a HOST fp64 "
+                      "evaluation of source/p3mMethod.cpp:240-245 (numpy), which pins the brute-force kernel itself"}
 
     # ---- like-for-like sibling of the reference arm (which can only afford N = 2^15 on the CPU)
     n_small = int(os.environ.get("P3M_BENCH_CPU_N", 1 << 15))
@@ -529,7 +543,7 @@ def run_ours(args):
     extra = {}
     if not args.no_extra:
         # the 1-GPU point of the coupled weak-scaling sweep that `--gpus N` (N > 1) reports (BASELINE configs[4])
-        prm5, ic5, grid5 = c5_setup(capi, 1)
+        prm5, ic5, grid5 = c5_setup(capi, 1, margin=uniform_margin_cells(args))
         r5 = run_single(args, capi, cu, prm5, ic5, "C5 at 1 GPU", flush, flush_bytes, want_e2e=False)
         c5 = r5["ctx"]
         ch5, in5 = c5.pair_counts()
@@ -576,7 +590,7 @@ def run_c3_single(args, capi, cu, flush, flush_bytes, hbm_peak, peak_src):
     (deposit, FFT, gather, sort, integrate) are the whole step.  Per-kernel HBM fractions."""
     n = int(os.environ.get("P3M_BENCH_N", 1 << 24))
     grid = int(os.environ.get("P3M_BENCH_GRID", 512))
-    prm, ic = c3_setup(capi, n, grid)
+    prm, ic = c3_setup(capi, n, grid, margin=uniform_margin_cells(args))
     r = run_single(args, capi, cu, prm, ic, "C3", flush, flush_bytes, want_e2e=False)
     st = r["ctx"].stats()
     r["ctx"].close()
@@ -634,6 +648,8 @@ def measure_multi(args, capi, pdist, dist, torch, cu, prm, ic, flush, flush_byte
     ctx.phase_ms(reset=True)
     launches0 = ctx.launches
     ms = timed_window(cu, ctx, steps, flush, flush_bytes, clocks, barrier=dist.barrier)
+    if ctx.escaped():
+        raise RuntimeError("a particle left the computational box during the timed steps: the measurement is void")
     ph = ctx.phase_ms(reset=True)
     launches = ctx.launches - launches0
     names = sorted(ph)
@@ -718,7 +734,8 @@ def run_ours_multi(args):
     if rank == 0:
         clocks.start()
     if args.config == "mesh":
-        prm, ic = c3_setup(capi, int(os.environ.get("P3M_BENCH_N", 1 << 24)), int(os.environ.get("P3M_BENCH_GRID", 512)), device=local)
+        prm, ic = c3_setup(capi, int(os.environ.get("P3M_BENCH_N", 1 << 24)), int(os.environ.get("P3M_BENCH_GRID", 512)), device=local,
+                           margin=uniform_margin_cells(args))
         workload = f"C3: PM uniform cube, {ic.n} particles, {prm.nx}^3 mesh, strong scaling over {world} GPUs"
         scaling = "strong"
     elif args.config == "c4":
@@ -728,7 +745,8 @@ def run_ours_multi(args):
     else:
         if world not in C5_GRIDS:
             raise SystemExit(f"--gpus {world}: the weak-scaling sweep is defined for 1/2/4/8 GPUs")
-        prm, ic, grid = c5_setup(capi, world, int(os.environ.get("P3M_BENCH_N", N_C5_PER_GPU)), device=local)
+        prm, ic, grid = c5_setup(capi, world, int(os.environ.get("P3M_BENCH_N", N_C5_PER_GPU)), device=local,
+                                 margin=uniform_margin_cells(args))
         workload = (f"C5 (BASELINE configs[4]): P3M weak-scaling sweep, 2^23 particles per GPU = {ic.n}, mesh "
                     f"{grid[0]}x{grid[1]}x{grid[2]}, ONE uniform distribution across all z-slabs (migration, ghost layers, "
                     f"plane exchanges and the slab FFT all active), TSC, S1-optimal Green, chaining-mesh PP (re=0.7a, a=3H)")
@@ -747,7 +765,8 @@ def run_ours_multi(args):
         # the 1-GPU point of the same sweep, measured in this run on rank 0 (the others wait), so that the line
         # carries its own weak-scaling baseline
         if rank == 0:
-            prm1, ic1, grid1 = c5_setup(capi, 1, int(os.environ.get("P3M_BENCH_N", N_C5_PER_GPU)), device=local)
+            prm1, ic1, grid1 = c5_setup(capi, 1, int(os.environ.get("P3M_BENCH_N", N_C5_PER_GPU)), device=local,
+                                        margin=uniform_margin_cells(args))
             r1 = run_single(args, capi, cu, prm1, ic1, "C5 at 1 GPU", flush, flush_bytes, want_e2e=False)
             r1["ctx"].close()
             v1 = ic1.n * args.steps / (float(np.sum(r1["ms"])) / 1e3)
@@ -757,7 +776,7 @@ def run_ours_multi(args):
         dist.barrier()
         if world == 8:
             for name, setup in (("c3", c3_setup), ("c4", c4_setup)):
-                sprm, sic = setup(capi, device=local)
+                sprm, sic = setup(capi, device=local, margin=uniform_margin_cells(args))
                 rr = measure_multi(args, capi, pdist, dist, torch, cu, sprm, sic, flush, flush_bytes,
                                    steps=max(args.steps, 10), want_e2e=False)
                 c2x = rr.pop("ctx")

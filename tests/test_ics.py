@@ -103,5 +103,11 @@ def test_generated_set_is_the_sampled_set_and_counter_based():
         assert np.array_equal(ga[0], gb[0]) and np.array_equal(ga[1], gb[1])
         a.force(); b.force()
         assert a.stats()["uniform_mass_table"] == 1.0
+        (pma, sra), (pmb, srb) = a.acc_parts(), b.acc_parts()
+        assert np.array_equal(sra, srb), "same particles, same order, same masses: the short-range sums are bit-identical"
+        assert rel_l2(a.density(), b.density()) < 1e-6
+        # the mesh part inherits the run-to-run REDG order of the P3M-context deposit (1e-7 on the density), amplified
+        # by the differencing of a potential that is ~1e4 times larger than its cell-to-cell change
+        assert rel_l2(pma, pmb) < 5e-3
         fa, fb = a.get_particles(capi.UNITS_CODE, want=("acc",))[2], b.get_particles(capi.UNITS_CODE, want=("acc",))[2]
-        assert rel_l2(fa, fb) < 1e-6
+        assert rel_l2(fa, fb) < 2e-4
