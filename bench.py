@@ -484,6 +484,19 @@ def run_ours(args):
     flush = cu.malloc(flush_bytes)
     if args.config == "mesh":
         return run_c3_single(args, capi, cu, flush, flush_bytes, hbm_peak, peak_src)
+    if args.config == "c5":
+        prm5, ic5, grid5 = c5_setup(capi, 1, int(os.environ.get("P3M_BENCH_N", N_C5_PER_GPU)), margin=uniform_margin_cells(args))
+        r5 = run_single(args, capi, cu, prm5, ic5, "C5 at 1 GPU", flush, flush_bytes, want_e2e=False)
+        ch5, in5 = r5["ctx"].pair_counts()
+        st5 = r5["ctx"].stats()
+        r5["ctx"].close()
+        print(json.dumps({"metric": "P3M particle-steps/s (secondary: 1-GPU point of the weak-scaling sweep)",
+                          "value": ic5.n * args.steps / (float(np.sum(r5["ms"])) / 1e3), "unit": "particle-steps/s", "n_gpus": 1,
+                          "ms_per_step": float(np.mean(r5["ms"])), "config": {"workload": f"C5 at 1 GPU: 2^23 particles, mesh {grid5}"},
+                          "ms_per_step_by_phase": {k: round(v, 4) for k, v in r5["phases"].items()},
+                          "pairs_in_range_per_particle": in5 / ic5.n, "pairs_checked_per_particle": ch5 / ic5.n, "stats": st5,
+                          "roofline_kernels": mesh_rooflines(ic5.n, grid5[0] * grid5[1] * grid5[2], r5["phases"], hbm_peak)}))
+        return
     n = int(os.environ.get("P3M_BENCH_N", N_C2))
     clocks = ClockSampler(0)
     clocks.start()
@@ -660,6 +673,8 @@ def measure_multi(args, capi, pdist, dist, torch, cu, prm, ic, flush, flush_byte
     total_ms = float(table[:, -1].max())                    # device time, max over ranks
     phases = {k: [round(float(table[:, i].min()), 4), round(float(np.median(table[:, i])), 4), round(float(table[:, i].max()), 4)]
               for i, k in enumerate(names)}
+    per_rank = {k: [round(float(x), 3) for x in table[:, i]] for i, k in enumerate(names)}
+    per_rank["step_total"] = [round(float(x) / steps, 3) for x in table[:, -1]]
     st = ctx.stats()
     keys = ("migrated", "ghosts", "a2a_bytes", "density_plane_bytes", "potential_plane_bytes", "migration_bytes", "ghost_bytes")
     sv = torch.tensor([st[k] for k in keys] + [float(ctx.n)], device="cuda", dtype=torch.float64)
@@ -679,7 +694,8 @@ def measure_multi(args, capi, pdist, dist, torch, cu, prm, ic, flush, flush_byte
                         "all-to-all transposes, escape-flag all-reduce) INCLUDING the wait for the slowest rank; the other "
                         "phases contain no collective"}
     out = {"ctx": ctx, "ms_per_step": total_ms / steps, "value": n_total * steps / (total_ms / 1e3), "phases": phases,
-           "exchange": exchange, "parity": parity, "launches": launches, "slab": bool(st["slab"]), "n_total": n_total}
+           "exchange": exchange, "parity": parity, "launches": launches, "slab": bool(st["slab"]), "n_total": n_total,
+           "per_rank": per_rank}
     if want_e2e:
         # every rank uploads the particles it holds (pinned host buffers, explicit ids), steps, and reads them back into
         # the other set of pinned buffers (ping-pong: no host-side copies in the loop)
@@ -730,9 +746,8 @@ def run_ours_multi(args):
     cu.set_device(local)
     flush_bytes = 256 << 20
     flush = cu.malloc(flush_bytes)
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
+    clocks = ClockSampler(local)   # every rank watches its own GPU
+    clocks.start()
     if args.config == "mesh":
         prm, ic = c3_setup(capi, int(os.environ.get("P3M_BENCH_N", 1 << 24)), int(os.environ.get("P3M_BENCH_GRID", 512)), device=local,
                            margin=uniform_margin_cells(args))
@@ -752,7 +767,15 @@ def run_ours_multi(args):
                     f"plane exchanges and the slab FFT all active), TSC, S1-optimal Green, chaining-mesh PP (re=0.7a, a=3H)")
         scaling = "weak"
     r = measure_multi(args, capi, pdist, dist, torch, cu, prm, ic, flush, flush_bytes, clocks)
-    clk = clocks.stop() if rank == 0 else None
+    clk_mine = clocks.stop()
+    clk_all = [None] * world
+    dist.all_gather_object(clk_all, clk_mine)
+    clk = dict(clk_all[0])
+    clk["per_rank"] = clk_all
+    clk["reasons"] = sorted({x for c_ in clk_all for x in (c_.get("reasons") or [])})
+    sm_all = [c_.get("sm_mhz") for c_ in clk_all if c_.get("sm_mhz")]
+    if sm_all:
+        clk["sm_mhz"] = float(min(sm_all))   # the slowest GPU of the job
     ctx = r.pop("ctx")
     pc = torch.tensor([0.0, 0.0], device="cuda", dtype=torch.float64)
     if prm.p3m:
@@ -806,7 +829,8 @@ def run_ours_multi(args):
                        "note": "N = 1 of this bench is BASELINE configs[1] (C2, a different workload); the 1-GPU point of THIS "
                                "sweep is extra.c5_n1 (also in the N = 1 line)"},
             "clocks": clk, "gpu_launches": r["launches"], "e2e": r.get("e2e"),
-            "ms_per_step_by_phase_min_median_max_over_ranks": r["phases"], "exchange": r["exchange"], "parity": r["parity"],
+            "ms_per_step_by_phase_min_median_max_over_ranks": r["phases"], "ms_per_step_by_phase_per_rank": r["per_rank"],
+            "exchange": r["exchange"], "parity": r["parity"],
             "pairs_in_range_per_particle": float(pc[1].item()) / r["n_total"],
             "pairs_checked_per_particle": float(pc[0].item()) / r["n_total"],
             "extra": extra, "roofline": None, "cpu_baseline": None,
@@ -825,7 +849,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra.* measurements (C5 at 1 GPU; C3 / C4 at 8 GPUs)")
-    ap.add_argument("--config", default="c2", choices=["c2", "mesh", "c4"],
+    ap.add_argument("--config", default="c2", choices=["c2", "mesh", "c4", "c5"],
                     help="c2 = the driver's contract: BASELINE configs[1] at 1 GPU, the coupled weak-scaling sweep configs[4] at "
                          "N > 1; mesh = configs[2] (PM, 2^24 particles, 512^3; 1 GPU or strong scaling under torchrun); c4 = "
                          "configs[3] (P3M clustered disk + halo, 2^26 particles, 1024^3 mesh; torchrun)")
@@ -835,7 +859,18 @@ def main():
             return
         run_reference(args)
         return
-    run_ours(args)
+    try:
+        run_ours(args)
+    except BaseException:
+        if int(os.environ.get("WORLD_SIZE", 1)) > 1:
+            # a failing rank must not linger in interpreter shutdown (destroying an NCCL communicator waits for
+            # peers that are themselves waiting in a collective): report and leave, torchrun ends the job
+            import traceback
+            traceback.print_exc()
+            sys.stderr.flush()
+            sys.stdout.flush()
+            os._exit(1)
+        raise
 
 
 if __name__ == "__main__":

@@ -27,6 +27,7 @@ void p3m_tune_load_impl(p3m_tune& t) {
   if (const char* e = getenv("P3M_TUNE_SUBBITS")) t.subbits = atoi(e);
   t.long_key = flag("P3M_TUNE_LONGKEY");
   t.old_deposit = flag("P3M_TUNE_OLD_DEPOSIT");
+  t.old_gather = flag("P3M_TUNE_OLD_GATHER");
   t.static_cuts = flag("P3M_STATIC_CUTS");
   t.count_cuts = flag("P3M_COUNT_CUTS");
   if (const char* e = getenv("P3M_TUNE_PARTICLE_WEIGHT")) t.particle_weight = atof(e);
@@ -36,6 +37,7 @@ void p3m_tune_load_impl(p3m_tune& t) {
   t.full_sort = flag("P3M_TUNE_FULL_SORT");
   t.scalar_pp = flag("P3M_TUNE_SCALAR_PP");
   if (const char* e = getenv("P3M_TUNE_A2A_CHUNKS")) t.a2a_chunks = atoi(e);
+  if (const char* e = getenv("P3M_TUNE_DENSE_CELL")) t.dense_cell = atoi(e) > 0 ? atoi(e) : 1;
 }
 
 static cudaEvent_t timer_event(PhaseTimer& t) {
@@ -143,6 +145,25 @@ static int setup_geometry(p3m_ctx* c) {
       best = b;
       break;
     }
+  }
+  // gather tile of P3M contexts: largest block whose footprint + 2-cell finite-difference halo fits kGatherTile^3
+  g.gshift = -1;
+  if (p.p3m) {
+    const int keep = g.bshift;
+    for (int b = g.mbits; b >= 0 && g.gshift < 0; --b) {
+      g.bshift = b;
+      const int B = 1 << b;
+      const int nb[3] = {(g.mx + B - 1) / B, (g.my + B - 1) / B, (g.mz + B - 1) / B};
+      bool ok = true;
+      for (int d = 0; d < 3 && ok; ++d)
+        for (int i = 0; i < nb[d] && ok; ++i) {
+          int lo[3], ext[3];
+          tile_box(g, d == 0 ? i : 0, d == 1 ? i : 0, d == 2 ? i : 0, lo, ext);
+          ok = ext[d] + 4 <= kGatherTile;
+        }
+      if (ok) g.gshift = b;
+    }
+    g.bshift = keep;
   }
   if (best < 0) {
     // a single binning cell is larger than the tile budget: direct paths only

@@ -81,6 +81,7 @@ struct p3m_tune {
   int subbits = -1;             // P3M_TUNE_SUBBITS: sub-cell bits of the P3M sort key (-1 = default)
   bool long_key = false;        // P3M_TUNE_LONGKEY: 64-bit sort key in PM-only contexts
   bool old_deposit = false;     // P3M_TUNE_OLD_DEPOSIT: warp-private-tile deposit in PM-only contexts
+  bool old_gather = false;      // P3M_TUNE_OLD_GATHER: round-1 gather kernel (E tile, synchronous staging) in P3M contexts
   bool static_cuts = false;     // P3M_STATIC_CUTS: geometric layer cuts
   bool count_cuts = false;      // P3M_COUNT_CUTS: cuts by particle count also for P3M
   double particle_weight = 300.0;  // P3M_TUNE_PARTICLE_WEIGHT: mesh-side work of a particle, in pair evaluations
@@ -90,6 +91,8 @@ struct p3m_tune {
   bool full_sort = false;       // P3M_TUNE_FULL_SORT: radix-sort from scratch every step
   bool scalar_pp = false;       // P3M_TUNE_SCALAR_PP: scalar-FFMA dense-cell kernel instead of the packed one
   int a2a_chunks = 0;           // P3M_TUNE_A2A_CHUNKS: plane chunks of the overlapped slab FFT (0 = default)
+  int dense_cell = p3m::kDenseCell;  // P3M_TUNE_DENSE_CELL: chaining cells with at least this many particles take the
+                                // warp-per-64-targets kernel, the others the thread-per-target kernel
   void load();
 };
 

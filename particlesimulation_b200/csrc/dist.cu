@@ -41,11 +41,11 @@ namespace p3m {
   } while (0)
 
 constexpr int kCntSeg = 0;     // [0..P]   segment starts of the destination-sorted particles
-constexpr int kCntMine = 16;   // [16..16+P) my per-destination counts
-constexpr int kCntAll = 32;    // [32..32+P*P) everybody's counts (row = source rank)
-constexpr int kCntGhost = 96;  // [96, 97] my ghost counts (to rank-1, to rank+1)
-constexpr int kCntGhostAll = 100;  // [100..100+2P) everybody's ghost counts
-constexpr int kCntTotal = 128;
+constexpr int kCntMine = 16;   // [16..16+P) my per-destination counts, [16+P] my particle capacity
+constexpr int kCntAll = 32;    // [32..32+P*(P+1)) everybody's counts + capacity (row = source rank, stride P+1)
+constexpr int kCntGhost = 112;  // [112, 113] my ghost counts (to rank-1, to rank+1), [114] my ghost receive capacity
+constexpr int kCntGhostAll = 116;  // [116..116+3P) everybody's ghost counts and capacities
+constexpr int kCntTotal = 160;
 
 template <typename T>
 static void set_cuts(p3m_ctx* c) {
@@ -248,7 +248,8 @@ __global__ void k_dest(const V4<T>* __restrict__ posm, long long n, Geom<T> g, u
   slots[i] = (uint32_t)i;
 }
 
-__global__ void k_seg_start(const uint32_t* __restrict__ dest_sorted, long long n, int P, int* __restrict__ cnt) {
+__global__ void k_seg_start(const uint32_t* __restrict__ dest_sorted, long long n, int P, int cap,
+                            int* __restrict__ cnt) {
   const int d = threadIdx.x;
   if (d > P) return;
   long long lo = 0, hi = n;
@@ -259,6 +260,7 @@ __global__ void k_seg_start(const uint32_t* __restrict__ dest_sorted, long long 
   cnt[kCntSeg + d] = (int)lo;
   __syncthreads();
   if (d < P) cnt[kCntMine + d] = cnt[kCntSeg + d + 1] - cnt[kCntSeg + d];
+  if (d == P) cnt[kCntMine + P] = cap;  // travels with the counts: capacities differ between ranks
 }
 
 template <typename T>
@@ -281,10 +283,11 @@ int dist_migrate(p3m_ctx* c, bool exchange) {
                                              bits, c->stream));
     c->launches += 3;
   }
-  k_seg_start<<<1, 32, 0, c->stream>>>(dest_sorted, n, P, c->dist_counts);
+  k_seg_start<<<1, 32, 0, c->stream>>>(dest_sorted, n, P, (int)(c->cap < 0x7fffffffLL ? c->cap : 0x7fffffffLL),
+                                       c->dist_counts);
   P3M_LAUNCH_CHECK(c);
   if (exchange) {
-    P3M_NCCL(ncclAllGather(c->dist_counts + kCntMine, c->dist_counts + kCntAll, P, ncclInt, comm, c->stream));
+    P3M_NCCL(ncclAllGather(c->dist_counts + kCntMine, c->dist_counts + kCntAll, P + 1, ncclInt, comm, c->stream));
     c->launches++;
   }
   P3M_CUDA(cudaMemcpyAsync(c->dist_counts_host, c->dist_counts, sizeof(int) * kCntTotal, cudaMemcpyDeviceToHost,
@@ -298,9 +301,10 @@ int dist_migrate(p3m_ctx* c, bool exchange) {
     // them fail together instead of one leaving the others waiting in a collective
     for (int dst = 0; dst < P; ++dst) {
       long long tot = 0;
-      for (int src = 0; src < P; ++src) tot += h[kCntAll + src * P + dst];
-      if (tot > c->cap)
-        return fail(P3M_ERANGE, "rank %d would hold %lld particles, capacity %lld", dst, tot, c->cap);
+      for (int src = 0; src < P; ++src) tot += h[kCntAll + src * (P + 1) + dst];
+      const long long cap_dst = h[kCntAll + dst * (P + 1) + P];
+      if (tot > cap_dst)
+        return fail(P3M_ERANGE, "rank %d would hold %lld particles, capacity %lld", dst, tot, cap_dst);
       if (dst == me) n_new = tot;
     }
   }
@@ -328,7 +332,7 @@ int dist_migrate(p3m_ctx* c, bool exchange) {
     P3M_NCCL(ncclGroupStart());
     for (int p = 0; p < P; ++p) {
       if (p == me) continue;
-      const long long ns = h[kCntMine + p], nr = h[kCntAll + p * P + me];
+      const long long ns = h[kCntMine + p], nr = h[kCntAll + p * (P + 1) + me];
       if (ns > 0) {
         P3M_NCCL(ncclSend(s.posm_alt + seg[p], sizeof(V4<T>) * ns, ncclChar, p, comm, c->stream));
         P3M_NCCL(ncclSend(s.vel_alt + seg[p], sizeof(V4<T>) * ns, ncclChar, p, comm, c->stream));
@@ -413,23 +417,30 @@ int dist_ghosts(p3m_ctx* c) {
   phase_begin(c, PH_COMM);
   const long long n = c->n, half = s.ghost_cap / 2;
   int* counters = c->dist_counts + kCntGhost;
-  P3M_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * 2, c->stream));
+  {
+    // [2] = how many ghosts this rank can receive; capacities differ between ranks after p3m_set_particles_ids
+    const long long rc = s.ghost_cap < 0x7fffffffLL ? s.ghost_cap : 0x7fffffffLL;
+    const int init[3] = {0, 0, (int)rc};
+    P3M_CUDA(cudaMemcpyAsync(counters, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  }
   if (n > 0) {
     k_ghost_pack<T><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(s.posm, s.id, n, g, s.gposm_alt, s.gid_alt,
                                                                        half, counters);
     P3M_LAUNCH_CHECK(c);
   }
-  P3M_NCCL(ncclAllGather(counters, c->dist_counts + kCntGhostAll, 2, ncclInt, comm, c->stream));
-  P3M_CUDA(cudaMemcpyAsync(c->dist_counts_host + kCntGhostAll, c->dist_counts + kCntGhostAll, sizeof(int) * 2 * P,
+  P3M_NCCL(ncclAllGather(counters, c->dist_counts + kCntGhostAll, 3, ncclInt, comm, c->stream));
+  P3M_CUDA(cudaMemcpyAsync(c->dist_counts_host + kCntGhostAll, c->dist_counts + kCntGhostAll, sizeof(int) * 3 * P,
                            cudaMemcpyDeviceToHost, c->stream));
   P3M_CUDA(cudaStreamSynchronize(c->stream));
   const int* h = c->dist_counts_host + kCntGhostAll;
-  const long long send_lo = h[2 * me], send_hi = h[2 * me + 1];
-  const long long recv_lo = me > 0 ? h[2 * (me - 1) + 1] : 0;      // rank-1's highest layer
-  const long long recv_hi = me < P - 1 ? h[2 * (me + 1)] : 0;      // rank+1's lowest layer
-  for (int r = 0; r < P; ++r)  // same verdict on every rank (capacities are equal by construction)
-    if (h[2 * r] > half || h[2 * r + 1] > half)
-      return fail(P3M_ERANGE, "ghost layer overflow on rank %d", r);
+  const long long send_lo = h[3 * me], send_hi = h[3 * me + 1];
+  const long long recv_lo = me > 0 ? h[3 * (me - 1) + 1] : 0;      // rank-1's highest layer
+  const long long recv_hi = me < P - 1 ? h[3 * (me + 1)] : 0;      // rank+1's lowest layer
+  for (int r = 0; r < P; ++r) {  // every rank reaches the same verdict about every rank: nobody is left in a collective
+    const long long in = (r > 0 ? h[3 * (r - 1) + 1] : 0) + (r < P - 1 ? h[3 * (r + 1)] : 0);
+    if (in > h[3 * r + 2])
+      return fail(P3M_ERANGE, "rank %d would receive %lld ghost particles, capacity %d", r, in, h[3 * r + 2]);
+  }
   P3M_NCCL(ncclGroupStart());
   if (me > 0) {
     if (send_lo > 0) {

@@ -352,6 +352,185 @@ k_gather_pm(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start, 
   cp_async_wait<0>();
 }
 
+// ---- P3M contexts: the same pipeline on blocks of chaining cells ---------------------------------------------
+// Particles are sorted by (Morton(chaining cell), sub-cell, id), so an aligned block of (1 << gshift)^3 chaining
+// cells is one contiguous run.  Its mesh footprint is not a fixed box (the chaining cell is box / M / H mesh
+// cells, ~2.1 with the demo parameters, not an integer), so origin and extent are evaluated per block
+// (tile_box) and the tile has a compile-time PITCH of kGatherTile in x and y: every stencil offset is still an
+// immediate.  Persistent CTAs, potential tile of the next block streaming in with cp.async while the current
+// block's particles are interpolated (fp32: two buffers; fp64: one, staged synchronously), finite differences
+// taken on the fly from the potential tile (no E tile), one barrier per block.  Replaces the round-1 k_gather
+// (synchronous staging, E tile, two barriers per block, 12 KB tiles sized for the deposit kernel).
+constexpr int kGatherP3mChunk = 4096;  // particles per work item: a heavy block (cluster core) is shared by many CTAs
+
+__global__ void k_occupied_p3m_blocks(const int* __restrict__ cell_start, long long ncells, int shift3,
+                                      int2* __restrict__ list, int* __restrict__ counter) {
+  const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long c0 = b << shift3;
+  if (c0 >= ncells) return;
+  const long long c1 = c0 + (1LL << shift3) < ncells ? c0 + (1LL << shift3) : ncells;
+  const int np = cell_start[c1] - cell_start[c0];
+  if (np <= 0) return;
+  const int chunks = (np + kGatherP3mChunk - 1) / kGatherP3mChunk;
+  const int at = atomicAdd(counter, chunks);
+  for (int k = 0; k < chunks; ++k) list[at + k] = make_int2((int)b, k);
+}
+
+template <typename T, int K, int FD, int NBUF>
+__global__ void __launch_bounds__(256, 2)
+k_gather_p3m(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start, const int2* __restrict__ list,
+             const int* __restrict__ counter, Geom<T> g, const T* __restrict__ phi, V4<T>* __restrict__ acc) {
+  constexpr int P = kGatherTile, ELEMS = P * P * P;
+  constexpr int SY = P, SZ = P * P;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* const sbuf0 = reinterpret_cast<T*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const long long ncells = 1LL << (3 * g.mbits);
+  const int shift3 = 3 * g.gshift;
+  const int nocc = *counter, G = gridDim.x;
+  const T scale = (K == 3) ? T(0.125) : T(1);
+  Geom<T> gb = g;
+  gb.bshift = g.gshift;
+
+  // tile origin (mesh cell of tile element 0) and staged extents of block `blk`
+  auto box_of = [&](int blk, int o[3], int w[3]) {
+    const uint32_t c0 = (uint32_t)blk << shift3;
+    int lo[3], ext[3];
+    tile_box(gb, (int)(compact3(c0) >> g.gshift), (int)(compact3(c0 >> 1) >> g.gshift),
+             (int)(compact3(c0 >> 2) >> g.gshift), lo, ext);
+    for (int d = 0; d < 3; ++d) o[d] = lo[d] - FD, w[d] = min(ext[d] + 2 * FD, P);
+  };
+  // one warp per tile row: the index arithmetic is per ROW (warp-uniform), the lanes copy consecutive cells
+  auto stage = [&](int blk, T* dst, bool async) {
+    int o[3], w[3];
+    box_of(blk, o, w);
+    const int rows = w[1] * w[2];
+    for (int r = wid; r < rows; r += 8) {
+      const int iz = r / w[1], iy = r - iz * w[1];
+      const int gy = wrap_idx(o[1] + iy, g.ny), gz = pot_plane(g, o[2] + iz);
+      T* drow = dst + iz * SZ + iy * SY;
+      if (lane < w[0]) {
+        if (gz < 0) {
+          drow[lane] = T(0);
+        } else {
+          const T* src = phi + ((long long)wrap_idx(o[0] + lane, g.nx) + (long long)gy * g.nx + (long long)gz * g.nx * g.ny);
+          if (!async) {
+            drow[lane] = *src;
+          } else if (sizeof(T) == 4) {
+            cp_async_4(drow + lane, src);
+          } else {
+            cp_async_4(reinterpret_cast<float*>(drow + lane), reinterpret_cast<const float*>(src));
+            cp_async_4(reinterpret_cast<float*>(drow + lane) + 1, reinterpret_cast<const float*>(src) + 1);
+          }
+        }
+      }
+    }
+  };
+  auto range_of = [&](int2 item, int& s, int& e) {
+    const long long c0 = (long long)item.x << shift3;
+    s = cell_start[c0] + item.y * kGatherP3mChunk;
+    e = min(s + kGatherP3mChunk, cell_start[c0 + (1LL << shift3) < ncells ? c0 + (1LL << shift3) : ncells]);
+  };
+
+  int w = blockIdx.x;
+  if (w >= nocc) return;
+  const int2 none = make_int2(-1, 0);
+  int2 item = list[w];
+  int2 item_n = w + G < nocc ? list[w + G] : none;
+  int blk = item.x, blk_n = item_n.x;
+  int s, e;
+  range_of(item, s, e);
+  if (NBUF == 2) {
+    stage(blk, sbuf0, true);
+    cp_async_commit();
+  }
+  for (int it = 0; w < nocc; w += G, ++it) {
+    T* sphi = sbuf0 + (NBUF == 2 ? (it & 1) * ELEMS : 0);
+    int s_n = 0, e_n = 0;
+    const int2 item_nn = w + 2 * G < nocc ? list[w + 2 * G] : none;
+    if (blk_n >= 0) range_of(item_n, s_n, e_n);
+    if (NBUF == 2) {
+      if (blk_n >= 0) stage(blk_n, sbuf0 + ((it & 1) ^ 1) * ELEMS, true);
+      cp_async_commit();
+    } else {
+      stage(blk, sphi, false);
+    }
+    int i = s + tid;
+    V4<T> pn = i < e ? posm[i] : V4<T>{0, 0, 0, 0};
+    if (NBUF == 2) cp_async_wait<1>();  // everything but the newest group: this block's tile has landed
+    __syncthreads();
+    int o[3], wv[3];
+    box_of(blk, o, wv);
+    const bool direct = e - s < kGatherPmDirect;
+    for (; i < e; i += 256) {
+      const V4<T> p = pn;
+      if (i + 256 < e) pn = posm[i + 256];
+      const Stencil<T, K> st = make_stencil<T, K>(p.x, p.y, p.z, p.w);
+      const int rx = st.x0 - o[0], ry = st.y0 - o[1], rz = st.z0 - o[2];
+      const bool fits = !direct && rx >= FD && ry >= FD && rz >= FD && rx + K + FD <= wv[0] && ry + K + FD <= wv[1] &&
+                        rz + K + FD <= wv[2] && st.x0 >= 0 && st.y0 >= 0 && st.z0 >= 0 && st.x0 + K <= g.nx &&
+                        st.y0 + K <= g.ny && st.z0 + K <= g.nz;
+      T ax = 0, ay = 0, az = 0;
+      if (fits) {
+        const T* base = sphi + (rz * P + ry) * P + rx;
+#pragma unroll
+        for (int a = 0; a < K; ++a)
+#pragma unroll
+          for (int b = 0; b < K; ++b)
+#pragma unroll
+            for (int cc = 0; cc < K; ++cc) {
+              const T* q = base + (cc * P + b) * P + a;
+              if (FD == 1) {
+                const T wgt = (st.wx[a] * st.wy[b]) * st.wz[cc];
+                ax += wgt * (q[1] - q[-1]), ay += wgt * (q[SY] - q[-SY]), az += wgt * (q[SZ] - q[-SZ]);
+              } else {
+                const T wgt = scale * ((st.wx[a] * st.wy[b]) * st.wz[cc]);
+                const T k = T(-1.0) / 12;
+                ax += wgt * (k * (-q[2] + 8 * q[1] - 8 * q[-1] + q[-2]));
+                ay += wgt * (k * (-q[2 * SY] + 8 * q[SY] - 8 * q[-SY] + q[-2 * SY]));
+                az += wgt * (k * (-q[2 * SZ] + 8 * q[SZ] - 8 * q[-SZ] + q[-2 * SZ]));
+              }
+            }
+        if (FD == 1) {
+          const T f = T(-0.5) * scale;
+          ax *= f, ay *= f, az *= f;
+        }
+      } else {
+        gather_direct<T, K, FD>(st, g, phi, ax, ay, az);
+      }
+      add_external(g, p.x, p.y, p.z, ax, ay, az);
+      acc[i] = V4<T>{ax, ay, az, 0};
+    }
+    __syncthreads();  // this buffer is overwritten next
+    item_n = item_nn;
+    blk = blk_n, blk_n = item_nn.x, s = s_n, e = e_n;
+  }
+  if (NBUF == 2) cp_async_wait<0>();
+}
+
+template <typename T, int K, int FD>
+static int launch_gather_p3m(p3m_ctx* c) {
+  State<T>& s = Sel<T>::st(c);
+  const Geom<T>& g = Sel<T>::g(c);
+  const long long ncells = 1LL << (3 * g.mbits);
+  const int shift3 = 3 * g.gshift;
+  const long long nblocks = (ncells + (1LL << shift3) - 1) >> shift3;
+  // work items (block, chunk of its particles) in pp_items, which the short-range kernels rebuild later for
+  // themselves: at most nblocks + n / kGatherP3mChunk pairs of ints, within its 2 * (cap / 64 + ncells + 16) ints
+  int2* list = reinterpret_cast<int2*>(s.pp_items);
+  int* counter = s.pp_counters + 7;
+  P3M_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), c->stream));
+  k_occupied_p3m_blocks<<<(unsigned)((nblocks + 255) / 256), 256, 0, c->stream>>>(s.cell_start, ncells, shift3, list, counter);
+  P3M_LAUNCH_CHECK(c);
+  constexpr int NBUF = sizeof(T) == 4 ? 2 : 1;
+  auto kern = k_gather_p3m<T, K, FD, NBUF>;
+  const size_t smem = (size_t)NBUF * sizeof(T) * kGatherTile * kGatherTile * kGatherTile;
+  P3M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<c->num_sms * 2, 256, smem, c->stream>>>(s.posm, s.cell_start, list, counter, g, s.pot_part, s.acc);
+  P3M_LAUNCH_CHECK(c);
+  return 0;
+}
+
 template <typename T, int K, int FD>
 static int launch_gather_pm(p3m_ctx* c) {
   State<T>& s = Sel<T>::st(c);
@@ -408,6 +587,15 @@ int gather(p3m_ctx* c) {
     else if (k == 2 && fd == 2) r = launch_gather_pm<T, 2, 2>(c);
     else if (k == 1 && fd == 1) r = launch_gather_pm<T, 1, 1>(c);
     else r = launch_gather_pm<T, 1, 2>(c);
+  } else if (c->n > 0 && g.p3m && g.gshift >= 0 && !c->tune.old_gather) {
+    const int k = g.is == P3M_TSC ? 3 : (g.is == P3M_CIC ? 2 : 1);
+    const int fd = g.fds == P3M_TWO_POINT ? 1 : 2;
+    if (k == 3 && fd == 1) r = launch_gather_p3m<T, 3, 1>(c);
+    else if (k == 3 && fd == 2) r = launch_gather_p3m<T, 3, 2>(c);
+    else if (k == 2 && fd == 1) r = launch_gather_p3m<T, 2, 1>(c);
+    else if (k == 2 && fd == 2) r = launch_gather_p3m<T, 2, 2>(c);
+    else if (k == 1 && fd == 1) r = launch_gather_p3m<T, 1, 1>(c);
+    else r = launch_gather_p3m<T, 1, 2>(c);
   } else if (c->n > 0) {
     const int k = g.is == P3M_TSC ? 3 : (g.is == P3M_CIC ? 2 : 1);
     const int fd = g.fds == P3M_TWO_POINT ? 1 : 2;

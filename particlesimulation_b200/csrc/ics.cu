@@ -273,7 +273,7 @@ int generate_particles(p3m_ctx* c, const p3m_ic* icp) {
   Geom<T>& g = Sel<T>::g(c);
   const T mf = c->f64 ? (T)c->mass_factor64 : (T)c->mass_factor32;
   const unsigned blocks = (unsigned)((n + 255) / 256);
-  long long n_local = n;
+  long long n_local = n, n_max = 0;
   if (c->nranks > 1 && n > 0) {
     // (1) work weights of the binning layers from the whole set, on this rank's own device
     dist_set_cuts(c);  // geometric cuts: defines how many layers are being cut
@@ -304,19 +304,25 @@ int generate_particles(p3m_ctx* c, const p3m_ic* icp) {
       P3M_CUDA(cudaFreeAsync(wdev, c->stream));
       P3M_TRY(dist_cuts_from_weights<T>(c, weight.data(), layers));
     }
-    // (2) how many particles fall into this rank's layers
-    int* counter = Sel<T>::st(c).pp_counters + 5;
-    P3M_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), c->stream));
-    k_ic_fill_local<T><<<blocks, 256, 0, c->stream>>>(ic, n, g, g.H, g.DT, mf, counter, 0, nullptr, nullptr, nullptr,
-                                                     nullptr, nullptr);
+    // (2) how many particles fall into every rank's layers (final cuts): this rank's own count, and the largest
+    // one, which sizes the arrays of EVERY rank -- equal capacities keep the migration / ghost-layer capacity
+    // checks symmetric, and a thin slab next to a cluster core receives that core's boundary layer as ghosts
+    unsigned* lcnt = nullptr;
+    P3M_CUDA(cudaMallocAsync((void**)&lcnt, sizeof(unsigned) * (size_t)layers, c->stream));
+    P3M_CUDA(cudaMemsetAsync(lcnt, 0, sizeof(unsigned) * (size_t)layers, c->stream));
+    k_ic_hist<T><<<blocks, 256, 0, c->stream>>>(ic, n, g, g.H, g.DT, mf, layers, 0, lcnt);
     P3M_LAUNCH_CHECK(c);
-    int h = 0;
-    P3M_CUDA(cudaMemcpyAsync(&h, counter, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    std::vector<unsigned> hl((size_t)layers);
+    P3M_CUDA(cudaMemcpyAsync(hl.data(), lcnt, sizeof(unsigned) * (size_t)layers, cudaMemcpyDeviceToHost, c->stream));
     P3M_CUDA(cudaStreamSynchronize(c->stream));
-    n_local = h;
+    P3M_CUDA(cudaFreeAsync(lcnt, c->stream));
+    long long per_rank[P3M_MAX_RANKS] = {0};
+    for (int z = 0; z < layers; ++z) per_rank[layer_owner(g, z)] += hl[(size_t)z];
+    n_local = per_rank[c->rank];
+    for (int r = 0; r < c->nranks; ++r) n_max = per_rank[r] > n_max ? per_rank[r] : n_max;
   }
-  // capacity: head-room for migration (a rank may hold up to ~1.5 x its initial share)
-  const long long want = c->nranks > 1 ? n_local + n_local / 2 + 4096 : n_local;
+  // capacity: head-room for migration (a rank may hold up to ~1.5 x the largest initial share)
+  const long long want = c->nranks > 1 ? n_max + n_max / 2 + 4096 : n_local;
   P3M_TRY(alloc_particles<T>(c, want));
   State<T>& s = Sel<T>::st(c);
   if (n > 0) {

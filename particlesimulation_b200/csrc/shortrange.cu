@@ -169,13 +169,13 @@ __device__ __forceinline__ void load_table(const T* __restrict__ g_tab, V2<T>* s
 
 // ---- work items for the dense cells ------------------------------------------------------------------
 template <typename T>
-__global__ void k_pp_items(const int* __restrict__ cell_start, Geom<T> g, int* __restrict__ items,
+__global__ void k_pp_items(const int* __restrict__ cell_start, Geom<T> g, int dense_cell, int* __restrict__ items,
                            unsigned* __restrict__ cost, int* __restrict__ counters) {
   const long long ncells = 1LL << (3 * g.mbits);
   long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (c >= ncells) return;
   const int s = cell_start[c], nq = cell_start[c + 1] - s;
-  if (nq < kDenseCell) return;
+  if (nq < dense_cell) return;
   const int cx = (int)compact3((uint32_t)c), cy = (int)compact3((uint32_t)c >> 1),
             cz = (int)compact3((uint32_t)c >> 2);
   long long src = 0;
@@ -600,7 +600,7 @@ k_pp_packed(const V4<float>* __restrict__ posm, const int* __restrict__ cell_sta
 template <typename T, bool TABLE, bool COUNT>
 __global__ void __launch_bounds__(128)
 k_pp_sparse(const V4<T>* __restrict__ posm, long long n, const int* __restrict__ cell_start,
-            const V4<T>* __restrict__ gposm, const int* __restrict__ gcell_start, Geom<T> g, SRParams<T> sp, const T* __restrict__ g_tab, V4<T>* __restrict__ acc,
+            const V4<T>* __restrict__ gposm, const int* __restrict__ gcell_start, Geom<T> g, int dense_cell, SRParams<T> sp, const T* __restrict__ g_tab, V4<T>* __restrict__ acc,
             V4<T>* __restrict__ acc_sr, unsigned long long* __restrict__ pair_counts) {
   __shared__ V2<T> s_tab[kSRTable];
   __shared__ unsigned s_tb[32];
@@ -617,7 +617,7 @@ k_pp_sparse(const V4<T>* __restrict__ posm, long long n, const int* __restrict__
   bool inside;
   bin_cell(g, p.x, p.y, p.z, cx, cy, cz, inside);
   const uint32_t q = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
-  if (cell_start[q + 1] - cell_start[q] >= kDenseCell) return;  // tiled kernel owns this cell
+  if (cell_start[q + 1] - cell_start[q] >= dense_cell) return;  // tiled kernel owns this cell
   T ax = 0, ay = 0, az = 0;
   unsigned n_in = 0;
   unsigned long long checked = 0;
@@ -732,7 +732,8 @@ static int run_pp(p3m_ctx* c) {
   const long long n = c->n;
   const long long ncells = 1LL << (3 * g.mbits);
   // upper bound on dense-cell work items: every dense cell holds >= kDenseCell particles
-  long long max_items = n / kPPTargets + (ncells < n / kDenseCell ? ncells : n / kDenseCell) + 16;
+  const int dense = c->tune.dense_cell;
+  long long max_items = n / kPPTargets + (ncells < n / dense ? ncells : n / dense) + 16;
   unsigned* cost = reinterpret_cast<unsigned*>(s.keys);  // sort scratch is free between bin_sort calls
   unsigned* cost_sorted = reinterpret_cast<unsigned*>(s.keys_alt);
   unsigned* idx = s.slots;
@@ -742,7 +743,7 @@ static int run_pp(p3m_ctx* c) {
   if (COUNT) P3M_CUDA(cudaMemsetAsync(s.pair_counts, 0, sizeof(unsigned long long) * 2, c->stream));
   k_iota_zero<T><<<(unsigned)((max_items + 255) / 256), 256, 0, c->stream>>>(idx, cost, max_items);
   P3M_LAUNCH_CHECK(c);
-  k_pp_items<T><<<(unsigned)((ncells + 255) / 256), 256, 0, c->stream>>>(s.cell_start, g, s.pp_items,
+  k_pp_items<T><<<(unsigned)((ncells + 255) / 256), 256, 0, c->stream>>>(s.cell_start, g, dense, s.pp_items,
                                                                          cost, s.pp_counters);
   P3M_LAUNCH_CHECK(c);
   size_t tmp = s.cub_tmp_bytes;
@@ -772,7 +773,7 @@ static int run_pp(p3m_ctx* c) {
     P3M_LAUNCH_CHECK(c);
   }
   k_pp_sparse<T, TABLE, COUNT><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(
-      s.posm, n, s.cell_start, s.gposm, s.gcell_start, g, sp, s.sr_table, s.acc, s.acc_sr, s.pair_counts);
+      s.posm, n, s.cell_start, s.gposm, s.gcell_start, g, dense, sp, s.sr_table, s.acc, s.acc_sr, s.pair_counts);
   P3M_LAUNCH_CHECK(c);
   return 0;
 }

@@ -19,6 +19,11 @@ from particlesimulation_b200 import dist as pdist  # noqa: E402
 from refapi import rel_l2  # noqa: E402
 
 
+def note(msg):
+    if dist.get_rank() == 0:
+        print("DIST_PROGRESS " + msg, flush=True)
+
+
 def allsum(a):
     t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
     dist.all_reduce(t)
@@ -27,6 +32,7 @@ def allsum(a):
 
 def run_case(name, p, pos, vel, mass, p3m, steps):
     rank, world = dist.get_rank(), dist.get_world_size()
+    note(name)
     prm = to_p3m(p, p3m=p3m, zero_degenerate=True)  # 0/0 modes of the optimal G set to 0
     prm.device = int(os.environ.get("LOCAL_RANK", 0))
     out = {}
@@ -72,10 +78,12 @@ def run_generated(name, p, ic, p3m):
     """Device-side initial conditions: every rank generates only its own z-slab (p3m_generate_particles); the
     union must be the sampled set, and the force must equal the single-GPU force on the uploaded set."""
     rank, world = dist.get_rank(), dist.get_world_size()
+    note(name)
     prm = to_p3m(p, p3m=p3m, zero_degenerate=True)
     prm.device = int(os.environ.get("LOCAL_RANK", 0))
     ctx = pdist.create_context(prm, capi)
     ctx.generate_particles(ic)
+    note(name + " generated")
     n_local0 = ctx.n
     counts = allsum(np.array([ctx.n], np.int64))
     gp = allsum(ctx.get_particles(capi.UNITS_ORIGINAL, want=("pos",))[0])
@@ -122,4 +130,13 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:
+        # a rank that fails must not linger in interpreter shutdown (destroying an NCCL communicator waits for the
+        # peers, which are themselves waiting in a collective): report and leave at once, torchrun ends the job
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        sys.stdout.flush()
+        os._exit(1)

@@ -31,7 +31,7 @@ def test_slab_decomposition_matches_single_gpu(world, mesh):
     env = dict(os.environ)
     if mesh == "replicated":
         env["P3M_REPLICATED_MESH"] = "1"
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("DIST_RESULTS ")][-1]
     for res in json.loads(line[len("DIST_RESULTS "):]):
