@@ -500,12 +500,18 @@ def run_ours(args):
     n = int(os.environ.get("P3M_BENCH_N", N_C2))
     clocks = ClockSampler(0)
     clocks.start()
-    r = run_single(args, capi, cu, c2_params(capi), c2_ic(capi, n), "C2", flush, flush_bytes, clocks=clocks)
+    r = run_single(args, capi, cu, c2_params(capi), c2_ic(capi, n), "C2", flush, flush_bytes, clocks=clocks,
+                   want_e2e=not args.quick)
     clk = clocks.stop()
     ctx, ms, phases = r["ctx"], r["ms"], r["phases"]
     total_ms = float(np.sum(ms))
     value = n * args.steps / (total_ms / 1e3)
     M = GRID_C2[0] * GRID_C2[1] * GRID_C2[2]
+    if args.quick:
+        print(json.dumps({"metric": "P3M particle-steps/s", "value": value, "ms_per_step": total_ms / args.steps, "quick": True,
+                          "ms_per_step_by_phase": phases}))
+        ctx.close()
+        return
 
     # ---- roofline of the dominant kernel: exact pair statistics from the counting instantiation (read-only)
     checked, inside = ctx.pair_counts()
@@ -848,6 +854,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="profiling runs: timed window only (no parity, companion, extras, CPU arm)")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra.* measurements (C5 at 1 GPU; C3 / C4 at 8 GPUs)")
     ap.add_argument("--config", default="c2", choices=["c2", "mesh", "c4", "c5"],
                     help="c2 = the driver's contract: BASELINE configs[1] at 1 GPU, the coupled weak-scaling sweep configs[4] at "

@@ -44,6 +44,12 @@ int alloc_particles(p3m_ctx* c, long long n) {
   P3M_TRY(dev_alloc(&s.keys_alt, scap));
   P3M_TRY(dev_alloc(&s.slots, scap));
   P3M_TRY(dev_alloc(&s.slots_alt, scap));
+  P3M_TRY(dev_alloc(&s.skeys, cap));
+  P3M_TRY(dev_alloc(&s.skeys_alt, cap));
+  P3M_TRY(dev_alloc(&s.inc_hist, 1024 * (size_t)(cap / 4096 + 2) + 1024));
+  if (!s.inc_counts) P3M_TRY(dev_alloc(&s.inc_counts, 8));
+  if (!s.inc_counts_host) P3M_CUDA(cudaMallocHost((void**)&s.inc_counts_host, sizeof(int) * 8));
+  c->order_valid = false;
   P3M_TRY(dev_alloc(&s.aabb, 2 * (cap / kPPSub + 8)));
   P3M_TRY(dev_alloc(&s.pp_items, 2 * (cap / kPPTargets + ((size_t)1 << (3 * Sel<T>::g(c).mbits)) + 16)));
   size_t tmp = 0;
@@ -112,6 +118,7 @@ int upload_particles(p3m_ctx* c, const float* pos, const float* vel, const float
   c->n_global = n;
   c->have_particles = true;
   c->sorted = false;
+  c->order_valid = false;
   c->have_acc = true;  // all zero, in upload order
   {
     // equal masses?  (positive floats order like their bit patterns)
@@ -326,24 +333,33 @@ int bin_sort(p3m_ctx* c) {
   if (n > 0) {
     const unsigned blocks = (unsigned)((n + 255) / 256);
     size_t tmp = s.cub_tmp_bytes;
-    if (short_key) {
-      k_keys<T, uint32_t><<<blocks, 256, 0, c->stream>>>(s.posm, s.id, n, g, keys32, s.slots, s.flags);
+    bool merged = false;
+    if (s.inc_backoff > 0) --s.inc_backoff;
+    else if (short_key && c->order_valid && !c->tune.full_sort && s.skeys_n == n && s.skeys_bits == keybits)
+      P3M_TRY(sort_incremental<T>(c, keybits, &merged));  // movers only (incsort.cu)
+    if (!merged) {
+      if (short_key) {
+        k_keys<T, uint32_t><<<blocks, 256, 0, c->stream>>>(s.posm, s.id, n, g, keys32, s.slots, s.flags);
+        P3M_LAUNCH_CHECK(c);
+        // sorted keys go straight into the persistent array the next (incremental) sort compares against
+        P3M_CUDA(cub::DeviceRadixSort::SortPairs(s.cub_tmp, tmp, keys32, s.skeys, s.slots, s.slots_alt, (int)n, 0,
+                                                 keybits, c->stream));
+      } else {
+        k_keys<T, uint64_t><<<blocks, 256, 0, c->stream>>>(s.posm, s.id, n, g, s.keys, s.slots, s.flags);
+        P3M_LAUNCH_CHECK(c);
+        P3M_CUDA(cub::DeviceRadixSort::SortPairs(s.cub_tmp, tmp, s.keys, s.keys_alt, s.slots, s.slots_alt,
+                                                 (int)n, 0, keybits, c->stream));
+      }
+      c->launches += (keybits + 7) / 8 + 1;
+      c->full_sorts++;
+      k_permute<T><<<blocks, 256, 0, c->stream>>>(s.slots_alt, n, s.posm, s.vel, s.id, s.posm_alt,
+                                                  s.vel_alt, s.id_alt);
       P3M_LAUNCH_CHECK(c);
-      P3M_CUDA(cub::DeviceRadixSort::SortPairs(s.cub_tmp, tmp, keys32, keys32_alt, s.slots, s.slots_alt, (int)n, 0,
-                                               keybits, c->stream));
-    } else {
-      k_keys<T, uint64_t><<<blocks, 256, 0, c->stream>>>(s.posm, s.id, n, g, s.keys, s.slots, s.flags);
-      P3M_LAUNCH_CHECK(c);
-      P3M_CUDA(cub::DeviceRadixSort::SortPairs(s.cub_tmp, tmp, s.keys, s.keys_alt, s.slots, s.slots_alt,
-                                               (int)n, 0, keybits, c->stream));
+      std::swap(s.posm, s.posm_alt);
+      std::swap(s.vel, s.vel_alt);
+      std::swap(s.id, s.id_alt);
     }
-    c->launches += (keybits + 7) / 8 + 1;
-    k_permute<T><<<blocks, 256, 0, c->stream>>>(s.slots_alt, n, s.posm, s.vel, s.id, s.posm_alt,
-                                                s.vel_alt, s.id_alt);
-    P3M_LAUNCH_CHECK(c);
-    std::swap(s.posm, s.posm_alt);
-    std::swap(s.vel, s.vel_alt);
-    std::swap(s.id, s.id_alt);
+    c->incr_sort = merged;
     c->have_acc = false;  // acc / acc_sr were not permuted: stale until the next gather
     if (g.p3m) {
       const long long tiles = (n + kPPSub - 1) / kPPSub;
@@ -352,7 +368,7 @@ int bin_sort(p3m_ctx* c) {
     }
   }
   if (short_key)
-    k_cell_start<uint32_t><<<(unsigned)((ncells + 1 + 255) / 256), 256, 0, c->stream>>>(keys32_alt, n, lowbits, ncells,
+    k_cell_start<uint32_t><<<(unsigned)((ncells + 1 + 255) / 256), 256, 0, c->stream>>>(s.skeys, n, lowbits, ncells,
                                                                                        s.cell_start);
   else
     k_cell_start<uint64_t><<<(unsigned)((ncells + 1 + 255) / 256), 256, 0, c->stream>>>(s.keys_alt, n, lowbits, ncells,
@@ -360,6 +376,8 @@ int bin_sort(p3m_ctx* c) {
   P3M_LAUNCH_CHECK(c);
   phase_end(c, PH_BINSORT);
   c->sorted = true;
+  c->order_valid = short_key && n > 0;
+  s.skeys_n = n, s.skeys_bits = keybits;
   if (c->nranks > 1) P3M_TRY(dist_ghosts<T>(c));  // boundary-layer particles of the neighbour slabs
   return 0;
 }
@@ -454,9 +472,10 @@ void free_state(p3m_ctx* c) {
   void* ptrs[] = {s.posm,   s.posm_alt,  s.vel,      s.vel_alt,  s.acc,        s.acc_sr,  s.id,
                   s.id_alt, s.keys,      s.keys_alt, s.slots,    s.slots_alt,  s.cub_tmp, s.cell_start,
                   s.density, s.potential, s.spectrum, s.green,    s.field,      s.sr_table, s.pp_items, s.aabb, s.gposm, s.gposm_alt, s.gid, s.gid_alt, s.gcell_start, s.gaabb,
-                  s.pp_counters, s.pair_counts, s.flags, s.diag};
+                  s.pp_counters, s.pair_counts, s.flags, s.diag, s.skeys, s.skeys_alt, s.inc_hist, s.inc_counts};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  if (s.inc_counts_host) cudaFreeHost(s.inc_counts_host);
   if (s.twiddle_z) cudaFree(s.twiddle_z);
   if (s.plans) {
     cufftDestroy(s.plan_fwd);

@@ -32,6 +32,15 @@ struct State {
   uint32_t *slots = nullptr, *slots_alt = nullptr;
   void* cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
+  // incremental re-sort (incsort.cu): the 32-bit keys the arrays are currently sorted by (kept from sort to sort),
+  // radix histograms of the mover sort, mover count (device + pinned host copy)
+  uint32_t *skeys = nullptr, *skeys_alt = nullptr;
+  long long skeys_n = -1;
+  int skeys_bits = 0;
+  int inc_backoff = 0;  // full sorts still to do before the incremental path is tried again
+  int* inc_hist = nullptr;
+  int* inc_counts = nullptr;
+  int* inc_counts_host = nullptr;
   int* cell_start = nullptr;  // (1 << 3*mbits) + 1 entries
   V4<T>* aabb = nullptr;      // 2 per kPPTile-particle tile: (lo.xyz, -), (hi.xyz, -)
   // ghost particles of the two neighbouring z-slabs (dist.cu), sorted by the same key
@@ -90,6 +99,8 @@ struct p3m_tune {
   bool cufft_z = false;         // P3M_TUNE_CUFFT_Z: z leg through cuFFT + multiply kernel
   bool full_sort = false;       // P3M_TUNE_FULL_SORT: radix-sort from scratch every step
   bool scalar_pp = false;       // P3M_TUNE_SCALAR_PP: scalar-FFMA dense-cell kernel instead of the packed one
+  int inc_sort_den = 12;        // P3M_TUNE_INC_SORT_DEN: the movers are merged when they are fewer than n / this, else full sort
+  bool z_wide = false;          // P3M_TUNE_Z_WIDE: twice the columns per CTA in k_poisson_z at nz >= 512 (128-byte runs, 1024 threads)
   int a2a_chunks = 0;           // P3M_TUNE_A2A_CHUNKS: plane chunks of the overlapped slab FFT (0 = default)
   int dense_cell = p3m::kDenseCell;  // P3M_TUNE_DENSE_CELL: chaining cells with at least this many particles take the
                                 // warp-per-64-targets kernel, the others the thread-per-target kernel
@@ -110,6 +121,9 @@ struct p3m_ctx {
   // velocities and ids but not the accelerations, so it clears this flag; p3m_gather (or p3m_short_range on
   // its own) sets it again.  p3m_kick, acceleration readbacks and diagnostics refuse to run without it.
   bool have_acc = false;
+  // the particle arrays are in the order of State::skeys (set by p3m_bin_sort with the 32-bit key, kept through
+  // drifts and migrations, cleared by uploads / generation): the next sort only has to merge the movers
+  bool order_valid = false;
   long long launches = 0;
   int steps_since_sort = 0;
   p3m::Geom<float> g32;
@@ -228,6 +242,8 @@ template <typename T> void slab_free(p3m_ctx* c);
 template <typename T> int slab_replan(p3m_ctx* c);           // after the layer cuts moved
 // dist.cu: equal-COUNT layer cuts from the full particle set every rank was handed (clustered sets)
 template <typename T> int dist_balance_cuts(p3m_ctx* c, const float* pos, long long n, int units);
+template <typename T> int sort_incremental(p3m_ctx* c, int keybits, bool* done);  // incsort.cu
+template <typename T> int migrate_sorted_keys(p3m_ctx* c, const uint32_t* stayer_slots, long long keep, long long n_new);
 template <typename T> int dist_cuts_from_weights(p3m_ctx* c, const double* weight, int layers);  // + slab_replan
 // ics.cu: device-side initial conditions
 template <typename T> int generate_particles(p3m_ctx* c, const p3m_ic* ic);

@@ -317,6 +317,9 @@ int dist_migrate(p3m_ctx* c, bool exchange) {
   }
   // stayers to the front of the primary arrays, arrivals appended behind them in source-rank order
   const long long keep = h[kCntMine + me];
+  // the keys the stayers are sorted by travel with them (incremental re-sort, incsort.cu)
+  if (exchange) P3M_TRY(migrate_sorted_keys<T>(c, s.slots_alt + seg[me], keep, n_new));
+  else c->order_valid = false;
   if (keep > 0) {
     P3M_CUDA(cudaMemcpyAsync(s.posm, s.posm_alt + seg[me], sizeof(V4<T>) * keep, cudaMemcpyDeviceToDevice, c->stream));
     P3M_CUDA(cudaMemcpyAsync(s.vel, s.vel_alt + seg[me], sizeof(V4<T>) * keep, cudaMemcpyDeviceToDevice, c->stream));

@@ -340,6 +340,7 @@ int generate_particles(p3m_ctx* c, const p3m_ic* icp) {
   c->n_global = n;
   c->have_particles = true;
   c->sorted = false;
+  c->order_valid = false;
   c->have_acc = true;
   // every particle carries total_mass / n: the equal-mass force table applies
   const float m = n > 0 ? ic.total_mass / (float)n : 0.f;

@@ -285,8 +285,12 @@ int fused_z_pass(p3m_ctx* c, void* spec, const T* green, long long ncols) {
     case 6: return launch_z<T, 6, 32>(c, spec, green, ncols);
     case 7: return launch_z<T, 7, 32>(c, spec, green, ncols);
     case 8: return launch_z<T, 8, D ? 8 : 16>(c, spec, green, ncols);
-    case 9: return launch_z<T, 9, D ? 4 : 8>(c, spec, green, ncols);
-    case 10: return launch_z<T, 10, 4>(c, spec, green, ncols);
+    case 9:
+      if (c->tune.z_wide && !D) return launch_z<T, 9, 16>(c, spec, green, ncols);  // 128-byte runs, 1024 threads
+      return launch_z<T, 9, D ? 4 : 8>(c, spec, green, ncols);
+    case 10:
+      if (c->tune.z_wide && !D) return launch_z<T, 10, 8>(c, spec, green, ncols);
+      return launch_z<T, 10, 4>(c, spec, green, ncols);
     default: return fail(P3M_EINVAL, "fused z pass: nz = %d is not a power of two in [16, 1024]", c->prm.nz);
   }
 }

@@ -11,17 +11,11 @@ namespace p3m {
 // KeyT = uint32_t (PM-only contexts): (Morton(tile), mesh cell in the tile) without the id; the radix sort
 // is stable, so ties keep their previous relative order (id order right after an upload).  Half the key
 // bytes and 4 instead of 7 radix passes on a 512^3 mesh.
-template <typename T, typename KeyT>
-__global__ void k_keys(const V4<T>* __restrict__ posm, const int* __restrict__ id, long long n,
-                       Geom<T> g, KeyT* __restrict__ keys, uint32_t* __restrict__ slots,
-                       int* __restrict__ flags) {
-  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  V4<T> p = posm[i];
+// (Morton(cell), sub-cell) code of a position, without the id bits
+template <typename T>
+__device__ __forceinline__ uint64_t cell_key(const Geom<T>& g, const V4<T>& p, bool& inside) {
   int cx, cy, cz;
-  bool inside;
   bin_cell(g, p.x, p.y, p.z, cx, cy, cz, inside);
-  if (!inside) flags[1] = 1;
   uint64_t m = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
   if (g.sbits && !g.p3m) {
     // PM only: the mesh cell inside the 8^3 tile, x fastest -- neighbouring lanes then touch
@@ -38,6 +32,18 @@ __global__ void k_keys(const V4<T>* __restrict__ posm, const int* __restrict__ i
     sx = min(max(sx, 0), S - 1), sy = min(max(sy, 0), S - 1), sz = min(max(sz, 0), S - 1);
     m = (m << (3 * g.sbits)) | morton3((uint32_t)sx, (uint32_t)sy, (uint32_t)sz);
   }
+  return m;
+}
+
+template <typename T, typename KeyT>
+__global__ void k_keys(const V4<T>* __restrict__ posm, const int* __restrict__ id, long long n,
+                       Geom<T> g, KeyT* __restrict__ keys, uint32_t* __restrict__ slots,
+                       int* __restrict__ flags) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool inside;
+  const uint64_t m = cell_key(g, posm[i], inside);
+  if (!inside) flags[1] = 1;
   if (sizeof(KeyT) == 8)
     keys[i] = (KeyT)((m << g.idbits) | (uint64_t)(uint32_t)id[i]);
   else

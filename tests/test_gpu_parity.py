@@ -622,6 +622,45 @@ def test_pm_short_key_sort_stays_sorted_over_steps():
     assert np.array_equal(orders[0], orders[1])
 
 
+@pytest.mark.parametrize("p3m,n,sigma", [(False, 20000, 0.08), (False, 300000, 0.03), (True, 20000, 0.01), (True, 200000, 0.005),
+                                         (False, 5000, 0.0)])
+def test_incremental_sort_equals_full_sort(monkeypatch, p3m, n, sigma):
+    """The per-step re-sort merges only the movers (incsort.cu: mover mask, hand-written radix sort of the movers,
+    rank merge).  Its result must be, element for element, what the stable full radix sort of every particle gives
+    (P3M_TUNE_FULL_SORT=1): same order after every step, same positions -- and it must really have been used."""
+    p, pos, vel, mass = uniform_case(n, gfunc=0) if not p3m else uniform_case(n)
+    rng = np.random.default_rng(7)
+    vel = (sigma * rng.standard_normal(vel.shape)).astype(np.float32)
+    runs = {}
+    monkeypatch.setenv("P3M_TUNE_INC_SORT_DEN", "3")  # merge up to n / 3 movers (default: n / 12, the measured break-even)
+    for name, env in (("incremental", None), ("full", "1")):
+        if env:
+            monkeypatch.setenv("P3M_TUNE_FULL_SORT", env)
+        else:
+            monkeypatch.delenv("P3M_TUNE_FULL_SORT", raising=False)
+        orders = []
+        with capi.Context(to_p3m(p, p3m=p3m)) as ctx:
+            ctx.set_particles(pos, vel, mass)
+            ctx.force()
+            ctx.kick(0.5)
+            for _ in range(6):
+                ctx.step(1)
+                _, _, order = ctx.cells()
+                orders.append(order.copy())
+            st = ctx.stats()
+            gpos = ctx.get_particles(capi.UNITS_CODE, want=("pos",))[0]
+        runs[name] = (orders, gpos, st)
+    monkeypatch.delenv("P3M_TUNE_FULL_SORT", raising=False)
+    inc, full = runs["incremental"], runs["full"]
+    assert inc[2]["incremental_sorts"] >= 5 and full[2]["incremental_sorts"] == 0, (inc[2], full[2])
+    assert 0 <= inc[2]["sort_movers"] <= n / 3 and (sigma == 0.0 or inc[2]["sort_movers"] > 0), inc[2]
+    for a, b in zip(inc[0], full[0]):
+        assert np.array_equal(np.sort(a), np.arange(n))
+        assert np.array_equal(a, b)
+    # same order every step => same arithmetic, up to the unordered floating-point REDs of the density flush
+    assert np.abs(inc[1] - full[1]).max() < 1e-4
+
+
 # ------------------------------------------------------------------------ round-2 additions (kernels)
 def test_packed_fp32_pp_kernel_matches_the_scalar_kernel_and_the_oracle(monkeypatch):
     """k_pp_packed (FADD2 / FMUL2 / FFMA2 pair body, the default for fp32 + table + equal masses) against

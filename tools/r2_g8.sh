@@ -4,8 +4,9 @@ set -u
 N=${1:-8}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
-/usr/bin/time -v timeout 420 $TR bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/r2_g${N}.log 2> gpurun_out/r2_g${N}.err
-echo "rc=$? elapsed: $(grep Elapsed gpurun_out/r2_g${N}.err)"
+SECONDS=0
+timeout 420 $TR bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/r2_g${N}.log 2> gpurun_out/r2_g${N}.err
+echo "rc=$? elapsed: ${SECONDS}s"
 grep -v "^\*\*\*\|OMP_NUM\|^$" gpurun_out/r2_g${N}.err | grep -v "^\s" | tail -15 | cut -c1-400
 python - $N <<'PY'
 import json, sys
