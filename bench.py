@@ -190,13 +190,15 @@ def c2_ic(capi, n):
 
 C5_GRIDS = {1: (256, 256, 256), 2: (256, 256, 512), 4: (512, 512, 256), 8: (512, 512, 512)}
 N_C5_PER_GPU = 1 << 23
-VEL_SIGMA_CELLS = 0.05   # velocity dispersion of the uniform sets, mesh cells per step
+VEL_SIGMA_CELLS = float(os.environ.get("P3M_BENCH_VEL_SIGMA", 0.05))   # velocity dispersion of the uniform sets, mesh cells per step
 
 
 def uniform_margin_cells(args):
     """Uniform sets drift freely (their self-gravity is negligible over a bench run): keep every particle
     inside the box for all the steps one context executes (warm-up + timed + end-to-end), 6 sigma."""
     total = args.warmup + 2 * max(args.steps, 10) + 4
+    if "P3M_BENCH_MARGIN" in os.environ:
+        return float(os.environ["P3M_BENCH_MARGIN"])
     return max(4.0, 6 * VEL_SIGMA_CELLS * total)
 
 

@@ -63,6 +63,45 @@ __device__ __forceinline__ void gather_direct(const Stencil<T, K>& s, const Geom
       }
 }
 
+// Interior particles that are not served from a shared-memory tile (sparse blocks): the same arithmetic as the
+// tile path, straight from the potential mesh in global memory / L2 with run-time strides -- one base pointer, no
+// per-point index arithmetic.  Returns false when the stencil + finite-difference halo touches the periodic wrap,
+// leaves the arrays or (several GPUs) the planes held locally: the caller then takes gather_direct.
+template <typename T, int K, int FD>
+__device__ __forceinline__ bool gather_interior(const Stencil<T, K>& s, const Geom<T>& g,
+                                                const T* __restrict__ phi, T& ax, T& ay, T& az) {
+  if (s.x0 < FD || s.y0 < FD || s.z0 < FD || s.x0 + K + FD > g.nx || s.y0 + K + FD > g.ny || s.z0 + K + FD > g.nz)
+    return false;
+  const int zl0 = pot_plane(g, s.z0 - FD), zl1 = pot_plane(g, s.z0 + K - 1 + FD);
+  if (zl0 < 0 || zl1 != zl0 + K - 1 + 2 * FD) return false;
+  const long long SY = g.nx, SZ = (long long)g.nx * g.ny;
+  const T* base = phi + s.x0 + (long long)s.y0 * SY + (long long)(zl0 + FD) * SZ;
+  const T scale = (K == 3) ? T(0.125) : T(1);
+#pragma unroll
+  for (int a = 0; a < K; ++a)
+#pragma unroll
+    for (int b = 0; b < K; ++b)
+#pragma unroll
+      for (int cc = 0; cc < K; ++cc) {
+        const T* q = base + a + b * SY + cc * SZ;
+        if (FD == 1) {
+          const T wgt = (s.wx[a] * s.wy[b]) * s.wz[cc];
+          ax += wgt * (q[1] - q[-1]), ay += wgt * (q[SY] - q[-SY]), az += wgt * (q[SZ] - q[-SZ]);
+        } else {
+          const T wgt = scale * ((s.wx[a] * s.wy[b]) * s.wz[cc]);
+          const T k = T(-1.0) / 12;
+          ax += wgt * (k * (-q[2] + 8 * q[1] - 8 * q[-1] + q[-2]));
+          ay += wgt * (k * (-q[2 * SY] + 8 * q[SY] - 8 * q[-SY] + q[-2 * SY]));
+          az += wgt * (k * (-q[2 * SZ] + 8 * q[SZ] - 8 * q[-SZ] + q[-2 * SZ]));
+        }
+      }
+  if (FD == 1) {
+    const T f = T(-0.5) * scale;
+    ax *= f, ay *= f, az *= f;
+  }
+  return true;
+}
+
 // externalField in original units -> code units (source/pmMethod.cpp:386-388,
 // source/externalFields.cpp:4-15, include/unitConversions.h:22-24)
 template <typename T>
@@ -211,7 +250,7 @@ struct PmTile {
   static constexpr int WX = TX + 2 * HALO;  // staged extent in x (<= PX)
   static constexpr int ELEMS = PX * PY * PZ;
 };
-constexpr int kGatherPmDirect = 48;  // blocks with fewer particles read the potential straight from L2
+constexpr int kGatherPmDirect = 24;  // blocks with fewer particles read the potential straight from L2
 
 // non-empty 16 x 16 x 8 blocks (4 consecutive binning cells), compacted
 __global__ void k_occupied_blocks(const int* __restrict__ cell_start, long long ncells, int* __restrict__ list,
@@ -340,7 +379,8 @@ k_gather_pm(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start, 
           const T f = T(-0.5) * scale;
           ax *= f, ay *= f, az *= f;
         }
-      } else {
+      } else if (!gather_interior<T, K, FD>(st, g, phi, ax, ay, az)) {
+        ax = ay = az = 0;
         gather_direct<T, K, FD>(st, g, phi, ax, ay, az);
       }
       add_external(g, p.x, p.y, p.z, ax, ay, az);
@@ -495,7 +535,8 @@ k_gather_p3m(const V4<T>* __restrict__ posm, const int* __restrict__ cell_start,
           const T f = T(-0.5) * scale;
           ax *= f, ay *= f, az *= f;
         }
-      } else {
+      } else if (!gather_interior<T, K, FD>(st, g, phi, ax, ay, az)) {
+        ax = ay = az = 0;
         gather_direct<T, K, FD>(st, g, phi, ax, ay, az);
       }
       add_external(g, p.x, p.y, p.z, ax, ay, az);
