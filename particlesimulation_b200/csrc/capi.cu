@@ -37,6 +37,7 @@ void p3m_tune_load_impl(p3m_tune& t) {
   t.full_sort = flag("P3M_TUNE_FULL_SORT");
   t.scalar_pp = flag("P3M_TUNE_SCALAR_PP");
   t.z_wide = flag("P3M_TUNE_Z_WIDE");
+  t.contig_slabs = flag("P3M_TUNE_CONTIG_SLABS");
   if (const char* e = getenv("P3M_TUNE_INC_SORT_DEN")) t.inc_sort_den = atoi(e) > 1 ? atoi(e) : 2;
   if (const char* e = getenv("P3M_TUNE_A2A_CHUNKS")) t.a2a_chunks = atoi(e);
   if (const char* e = getenv("P3M_TUNE_DENSE_CELL")) t.dense_cell = atoi(e) > 0 ? atoi(e) : 1;

@@ -96,6 +96,7 @@ struct p3m_tune {
   double particle_weight = 300.0;  // P3M_TUNE_PARTICLE_WEIGHT: mesh-side work of a particle, in pair evaluations
   long long fft_chunk_bytes = 1ll << 60;  // P3M_TUNE_FFT_CHUNK_MB: split the 2-D plane batches
   bool replicated_mesh = false; // P3M_REPLICATED_MESH: full mesh + all-reduce instead of slabs
+  bool contig_slabs = false;    // P3M_TUNE_CONTIG_SLABS: one contiguous run of planes per rank (round-1 FFT slab layout)
   bool cufft_z = false;         // P3M_TUNE_CUFFT_Z: z leg through cuFFT + multiply kernel
   bool full_sort = false;       // P3M_TUNE_FULL_SORT: radix-sort from scratch every step
   bool scalar_pp = false;       // P3M_TUNE_SCALAR_PP: scalar-FFMA dense-cell kernel instead of the packed one
@@ -156,6 +157,7 @@ struct p3m_ctx {
   long long n_global = 0;
   bool fused_z = false;       // z leg of the Poisson solve = k_poisson_z (power-of-two nz), else cuFFT
   bool slab = false;          // slab-decomposed mesh + distributed FFT (else: replicated mesh, all-reduce)
+  bool slab_split = false;    // every rank's FFT slab = one run of planes in the occupied half + one in the padding half
   // static plane ranges of every rank (identical on all ranks): density planes deposited by the
   // particle slab, unwrapped potential planes its gather needs
   int den_z0[P3M_MAX_RANKS] = {0}, den_nz[P3M_MAX_RANKS] = {0}, pot_z0[P3M_MAX_RANKS] = {0}, pot_nz[P3M_MAX_RANKS] = {0};

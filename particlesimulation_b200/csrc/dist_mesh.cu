@@ -92,6 +92,26 @@ inline int grid_for(long long count, int sms) {
 
 }  // namespace
 
+// ---- which planes a rank's FFT slab holds ------------------------------------------------------------------------
+// The particles live in the lower half of the mesh along every axis (isolated boundary conditions by zero padding:
+// mesh = 2 x box), so with contiguous FFT slabs the upper half of the ranks would own nothing but empty planes while
+// the density of everybody's particles travels to the lower half and the potential back.  Each rank therefore owns
+// TWO runs of nzl / 2 planes: run 0 in the occupied half, [r h, (r+1) h), next to its own particles for count-
+// balanced cuts, and run 1 in the padding half, [nz/2 + r h, nz/2 + (r+1) h), h = nzl / 2 (`split`; odd nzl: one
+// contiguous run as before).  Local plane zl < h belongs to run 0, the others to run 1.
+struct SlabRuns {
+  int nruns, len;      // runs per rank, planes per run
+  int nz, nzl;
+  __host__ __device__ int first(int rank, int run) const { return nruns == 1 ? rank * nzl : (run == 0 ? rank * len : nz / 2 + rank * len); }
+};
+static SlabRuns slab_runs(const p3m_ctx* c, int nz) {
+  SlabRuns r;
+  r.nz = nz, r.nzl = nz / c->nranks;
+  const bool split = c->slab_split;
+  r.nruns = split ? 2 : 1, r.len = split ? r.nzl / 2 : r.nzl;
+  return r;
+}
+
 // ---- static plane ranges -------------------------------------------------------------------------------------
 template <typename T>
 static void plane_ranges(p3m_ctx* c) {
@@ -122,12 +142,15 @@ static void plane_ranges(p3m_ctx* c) {
 // my FFT slab.  With work-balanced cuts several thin particle slabs (each with its own halo planes) can sit
 // inside one FFT slab, so this is computed from the ranges instead of bounded by a formula.
 static size_t stage_planes_needed(const p3m_ctx* c, int nzl) {
+  const SlabRuns sr = slab_runs(c, nzl * c->nranks);
   size_t need = 0;
   for (int p = 0; p < c->nranks; ++p) {
     if (p == c->rank) continue;
-    const int lo = std::max(c->den_z0[p], c->rank * nzl);
-    const int hi = std::min(c->den_z0[p] + c->den_nz[p], (c->rank + 1) * nzl);
-    if (hi > lo) need += (size_t)(hi - lo);
+    for (int run = 0; run < sr.nruns; ++run) {
+      const int lo = std::max(c->den_z0[p], sr.first(c->rank, run));
+      const int hi = std::min(c->den_z0[p] + c->den_nz[p], sr.first(c->rank, run) + sr.len);
+      if (hi > lo) need += (size_t)(hi - lo);
+    }
   }
   return need + 1;
 }
@@ -237,41 +260,48 @@ int slab_reduce_density(p3m_ctx* c) {
   const size_t plane = (size_t)g.nx * g.ny;
   ncclComm_t comm = (ncclComm_t)c->nccl_comm;
   phase_begin(c, PH_COMM);
-  auto overlap = [&](int src, int dst, int& lo, int& hi) {
-    lo = std::max(c->den_z0[src], dst * nzl);
-    hi = std::min(c->den_z0[src] + c->den_nz[src], (dst + 1) * nzl);
+  const SlabRuns sr = slab_runs(c, g.nz);
+  // planes of the deposit range of particle rank `src` that fall into run `run` of the FFT slab of rank `dst`
+  auto overlap = [&](int src, int dst, int run, int& lo, int& hi) {
+    lo = std::max(c->den_z0[src], sr.first(dst, run));
+    hi = std::min(c->den_z0[src] + c->den_nz[src], sr.first(dst, run) + sr.len);
     return hi > lo;
   };
   P3M_CUDA(cudaMemsetAsync(s.density, 0, sizeof(T) * plane * nzl, c->stream));
-  size_t stage_off[P3M_MAX_RANKS] = {0};
+  size_t stage_off[P3M_MAX_RANKS][2] = {{0}};
   size_t off = 0;
   double sent = 0;
   P3M_NCCL(ncclGroupStart());
   for (int p = 0; p < P; ++p) {
     if (p == me) continue;
-    int lo, hi;
-    if (overlap(me, p, lo, hi)) sent += (double)(hi - lo) * (double)plane * sizeof(T);
-    if (overlap(me, p, lo, hi))
-      P3M_NCCL(ncclSend(s.dens_part + (size_t)(lo - c->den_z0[me]) * plane, (size_t)(hi - lo) * plane, nccl_real<T>(), p,
-                        comm, c->stream));
-    if (overlap(p, me, lo, hi)) {
-      stage_off[p] = off;
-      P3M_NCCL(ncclRecv(s.den_stage + off, (size_t)(hi - lo) * plane, nccl_real<T>(), p, comm, c->stream));
-      off += (size_t)(hi - lo) * plane;
+    for (int run = 0; run < sr.nruns; ++run) {
+      int lo, hi;
+      if (overlap(me, p, run, lo, hi)) {
+        sent += (double)(hi - lo) * (double)plane * sizeof(T);
+        P3M_NCCL(ncclSend(s.dens_part + (size_t)(lo - c->den_z0[me]) * plane, (size_t)(hi - lo) * plane, nccl_real<T>(), p,
+                          comm, c->stream));
+      }
+      if (overlap(p, me, run, lo, hi)) {
+        stage_off[p][run] = off;
+        P3M_NCCL(ncclRecv(s.den_stage + off, (size_t)(hi - lo) * plane, nccl_real<T>(), p, comm, c->stream));
+        off += (size_t)(hi - lo) * plane;
+      }
     }
   }
   P3M_NCCL(ncclGroupEnd());
   c->launches++;
   c->stat_den_bytes = sent;
   // sum in rank order: bit-reproducible
-  for (int p = 0; p < P; ++p) {
-    int lo, hi;
-    if (!overlap(p, me, lo, hi)) continue;
-    const T* src = p == me ? s.dens_part + (size_t)(lo - c->den_z0[me]) * plane : s.den_stage + stage_off[p];
-    const long long cnt = (long long)(hi - lo) * (long long)plane;
-    k_add_planes<T><<<grid_for(cnt, c->num_sms), 256, 0, c->stream>>>(s.density + (size_t)(lo - me * nzl) * plane, src, cnt);
-    P3M_LAUNCH_CHECK(c);
-  }
+  for (int p = 0; p < P; ++p)
+    for (int run = 0; run < sr.nruns; ++run) {
+      int lo, hi;
+      if (!overlap(p, me, run, lo, hi)) continue;
+      const T* src = p == me ? s.dens_part + (size_t)(lo - c->den_z0[me]) * plane : s.den_stage + stage_off[p][run];
+      const long long cnt = (long long)(hi - lo) * (long long)plane;
+      const size_t local = (size_t)(run * sr.len + lo - sr.first(me, run));  // local plane of global plane lo
+      k_add_planes<T><<<grid_for(cnt, c->num_sms), 256, 0, c->stream>>>(s.density + local * plane, src, cnt);
+      P3M_LAUNCH_CHECK(c);
+    }
   phase_end(c, PH_COMM);
   return 0;
 }
@@ -285,54 +315,78 @@ int slab_spread_potential(p3m_ctx* c) {
   const size_t plane = (size_t)g.nx * g.ny;
   ncclComm_t comm = (ncclComm_t)c->nccl_comm;
   phase_begin(c, PH_COMM);
-  // planes of owner `own`, periodic image k, wanted by particle rank `dst`: unwrapped [lo, hi)
-  auto overlap = [&](int own, int k, int dst, int& lo, int& hi) {
-    lo = std::max(own * nzl + k * g.nz, c->pot_z0[dst]);
-    hi = std::min((own + 1) * nzl + k * g.nz, c->pot_z0[dst] + c->pot_nz[dst]);
+  const SlabRuns sr = slab_runs(c, g.nz);
+  // planes of run `run` of owner `own`, periodic image k, wanted by particle rank `dst`: unwrapped [lo, hi)
+  auto overlap = [&](int own, int run, int k, int dst, int& lo, int& hi) {
+    lo = std::max(sr.first(own, run) + k * g.nz, c->pot_z0[dst]);
+    hi = std::min(sr.first(own, run) + sr.len + k * g.nz, c->pot_z0[dst] + c->pot_nz[dst]);
     return hi > lo;
   };
+  // local plane (in the slab of `own`) of unwrapped plane z of image k
+  auto local_of = [&](int own, int run, int k, int z) { return (size_t)(run * sr.len + z - k * g.nz - sr.first(own, run)); };
   double sent = 0;
   P3M_NCCL(ncclGroupStart());
   for (int p = 0; p < P; ++p)
-    for (int k = -1; k <= 1; ++k) {
-      int lo, hi;
-      if (p != me && overlap(me, k, p, lo, hi)) sent += (double)(hi - lo) * (double)plane * sizeof(T);
-      if (p != me && overlap(me, k, p, lo, hi))
-        P3M_NCCL(ncclSend(s.potential + (size_t)(lo - k * g.nz - me * nzl) * plane, (size_t)(hi - lo) * plane,
-                          nccl_real<T>(), p, comm, c->stream));
-      if (p != me && overlap(p, k, me, lo, hi))
-        P3M_NCCL(ncclRecv(s.pot_part + (size_t)(lo - c->pot_z0[me]) * plane, (size_t)(hi - lo) * plane, nccl_real<T>(),
-                          p, comm, c->stream));
-    }
+    for (int run = 0; run < sr.nruns; ++run)
+      for (int k = -1; k <= 1; ++k) {
+        int lo, hi;
+        if (p != me && overlap(me, run, k, p, lo, hi)) {
+          sent += (double)(hi - lo) * (double)plane * sizeof(T);
+          P3M_NCCL(ncclSend(s.potential + local_of(me, run, k, lo) * plane, (size_t)(hi - lo) * plane, nccl_real<T>(), p,
+                            comm, c->stream));
+        }
+        if (p != me && overlap(p, run, k, me, lo, hi))
+          P3M_NCCL(ncclRecv(s.pot_part + (size_t)(lo - c->pot_z0[me]) * plane, (size_t)(hi - lo) * plane, nccl_real<T>(),
+                            p, comm, c->stream));
+      }
   P3M_NCCL(ncclGroupEnd());
   c->launches++;
   c->stat_pot_bytes = sent;
-  for (int k = -1; k <= 1; ++k) {
-    int lo, hi;
-    if (overlap(me, k, me, lo, hi))
-      P3M_CUDA(cudaMemcpyAsync(s.pot_part + (size_t)(lo - c->pot_z0[me]) * plane,
-                               s.potential + (size_t)(lo - k * g.nz - me * nzl) * plane, sizeof(T) * (size_t)(hi - lo) * plane,
-                               cudaMemcpyDeviceToDevice, c->stream));
-  }
+  for (int run = 0; run < sr.nruns; ++run)
+    for (int k = -1; k <= 1; ++k) {
+      int lo, hi;
+      if (overlap(me, run, k, me, lo, hi))
+        P3M_CUDA(cudaMemcpyAsync(s.pot_part + (size_t)(lo - c->pot_z0[me]) * plane, s.potential + local_of(me, run, k, lo) * plane,
+                                 sizeof(T) * (size_t)(hi - lo) * plane, cudaMemcpyDeviceToDevice, c->stream));
+    }
   phase_end(c, PH_COMM);
   return 0;
 }
 
 // ---- the distributed Poisson solve ----------------------------------------------------------------------------------
+// Chunk p of the packed array = [run][plane in run][ky_local][kx] for / from rank p.  In the transposed array
+// [kz][ky_local][kx] the planes of run `run` of rank p start at kz = first(p, run): with split slabs a peer's chunk
+// lands in two places.  to_t: packed planes -> transposed array; else the way back.
 template <typename T>
-static int all_to_all(p3m_ctx* c, typename State<T>::cplx* send, typename State<T>::cplx* recv, size_t chunk) {
+static int all_to_all(p3m_ctx* c, typename State<T>::cplx* packed, typename State<T>::cplx* transposed, size_t chunk,
+                      bool to_t) {
   using cplx = typename State<T>::cplx;
   const int P = c->nranks, me = c->rank;
+  const SlabRuns sr = slab_runs(c, c->prm.nz);
+  const size_t part = chunk / (size_t)sr.nruns;          // elements of one run of one chunk
+  const size_t per_plane = chunk / (size_t)sr.nzl;       // nxh * nyl
   ncclComm_t comm = (ncclComm_t)c->nccl_comm;
   P3M_NCCL(ncclGroupStart());
   for (int p = 0; p < P; ++p) {
     if (p == me) continue;
-    P3M_NCCL(ncclSend(send + (size_t)p * chunk, chunk * sizeof(cplx), ncclChar, p, comm, c->stream));
-    P3M_NCCL(ncclRecv(recv + (size_t)p * chunk, chunk * sizeof(cplx), ncclChar, p, comm, c->stream));
+    for (int run = 0; run < sr.nruns; ++run) {
+      cplx* pk = packed + (size_t)p * chunk + (size_t)run * part;             // my planes of this run, rows of rank p
+      cplx* tr = transposed + (size_t)sr.first(p, run) * per_plane;           // planes of rank p's run, my rows
+      if (to_t) {
+        P3M_NCCL(ncclSend(pk, part * sizeof(cplx), ncclChar, p, comm, c->stream));
+        P3M_NCCL(ncclRecv(tr, part * sizeof(cplx), ncclChar, p, comm, c->stream));
+      } else {
+        P3M_NCCL(ncclSend(tr, part * sizeof(cplx), ncclChar, p, comm, c->stream));
+        P3M_NCCL(ncclRecv(pk, part * sizeof(cplx), ncclChar, p, comm, c->stream));
+      }
+    }
   }
   P3M_NCCL(ncclGroupEnd());
-  P3M_CUDA(cudaMemcpyAsync(recv + (size_t)me * chunk, send + (size_t)me * chunk, chunk * sizeof(cplx),
-                           cudaMemcpyDeviceToDevice, c->stream));
+  for (int run = 0; run < sr.nruns; ++run) {
+    cplx* pk = packed + (size_t)me * chunk + (size_t)run * part;
+    cplx* tr = transposed + (size_t)sr.first(me, run) * per_plane;
+    P3M_CUDA(cudaMemcpyAsync(to_t ? tr : pk, to_t ? pk : tr, part * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream));
+  }
   c->launches += 2;
   c->stat_a2a_bytes += (double)(P - 1) * (double)chunk * sizeof(cplx);
   return 0;
@@ -360,7 +414,7 @@ int slab_poisson(p3m_ctx* c) {
   c->launches += 1;
   phase_end(c, PH_FFT_FWD);
   phase_begin(c, PH_COMM);
-  P3M_TRY(all_to_all<T>(c, s.pack, s.spectrum_t, chunk));  // chunk p = planes of rank p: [kx, ky_local, z]
+  P3M_TRY(all_to_all<T>(c, s.pack, s.spectrum_t, chunk, true));  // chunk p = planes of rank p: [kx, ky_local, z]
   phase_end(c, PH_COMM);
   if (c->fused_z) {
     phase_begin(c, PH_MULTIPLY);  // forward z FFT + multiply + inverse z FFT in one pass (poisson_z.cu)
@@ -381,7 +435,7 @@ int slab_poisson(p3m_ctx* c) {
     phase_end(c, PH_FFT_INV);
   }
   phase_begin(c, PH_COMM);
-  P3M_TRY(all_to_all<T>(c, s.spectrum_t, s.pack, chunk));  // chunk p of the transposed array = planes of rank p
+  P3M_TRY(all_to_all<T>(c, s.pack, s.spectrum_t, chunk, false));  // planes of rank p in the transposed array -> chunk p
   phase_end(c, PH_COMM);
   phase_begin(c, PH_FFT_INV);
   k_transpose_pack<cplx, false><<<grid, 256, 0, c->stream>>>(s.spectrum, s.pack, nxh, g.ny, nyl, nzl);

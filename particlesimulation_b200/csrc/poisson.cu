@@ -275,6 +275,8 @@ int alloc_meshes(p3m_ctx* c) {
   const long long hc = half_count(p);
   // several ranks: slab-decomposed mesh whenever the planes and the ky rows divide evenly
   c->slab = c->nranks > 1 && p.nz % c->nranks == 0 && p.ny % c->nranks == 0 && !c->tune.replicated_mesh;
+  // every rank owns a run of planes in the occupied half of the mesh and one in the zero-padding half (dist_mesh.cu)
+  c->slab_split = c->slab && (p.nz / c->nranks) % 2 == 0 && !c->tune.contig_slabs;
   c->fused_z = fused_z_supported(p.nz) && !c->tune.cufft_z;
   if (c->fused_z) P3M_TRY(fused_z_init<T>(c));
   if (c->slab) {
@@ -380,7 +382,13 @@ int get_mesh(p3m_ctx* c, const T* dev, O* out, long long count) {
   if (c->slab) {
     const long long share = count / c->nranks;
     P3M_CUDA(cudaMemsetAsync(stage, 0, sizeof(O) * (size_t)count, c->stream));
-    k_convert<T, O><<<(unsigned)((share + 255) / 256), 256, 0, c->stream>>>(dev, stage + share * c->rank, share);
+    if (c->slab_split) {  // run 0 in the lower half, run 1 in the upper half of the full array
+      const long long half = share / 2;
+      k_convert<T, O><<<(unsigned)((half + 255) / 256), 256, 0, c->stream>>>(dev, stage + half * c->rank, half);
+      k_convert<T, O><<<(unsigned)((half + 255) / 256), 256, 0, c->stream>>>(dev + half, stage + count / 2 + half * c->rank, half);
+    } else {
+      k_convert<T, O><<<(unsigned)((share + 255) / 256), 256, 0, c->stream>>>(dev, stage + share * c->rank, share);
+    }
   } else {
     k_convert<T, O><<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(dev, stage, count);
   }
@@ -398,7 +406,13 @@ int set_mesh(p3m_ctx* c, T* dev, const I* in, long long count) {
   P3M_CUDA(cudaMemcpyAsync(stage, in, sizeof(I) * (size_t)count, cudaMemcpyHostToDevice, c->stream));
   if (c->slab) {  // keep this rank's planes of the full array
     const long long share = count / c->nranks;
-    k_convert<I, T><<<(unsigned)((share + 255) / 256), 256, 0, c->stream>>>(stage + share * c->rank, dev, share);
+    if (c->slab_split) {
+      const long long half = share / 2;
+      k_convert<I, T><<<(unsigned)((half + 255) / 256), 256, 0, c->stream>>>(stage + half * c->rank, dev, half);
+      k_convert<I, T><<<(unsigned)((half + 255) / 256), 256, 0, c->stream>>>(stage + count / 2 + half * c->rank, dev + half, half);
+    } else {
+      k_convert<I, T><<<(unsigned)((share + 255) / 256), 256, 0, c->stream>>>(stage + share * c->rank, dev, share);
+    }
   } else {
     k_convert<I, T><<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(stage, dev, count);
   }
