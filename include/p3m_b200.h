@@ -275,9 +275,14 @@ int p3m_get_sample(p3m_ctx* ctx, const int32_t* ids_ascending, int64_t m, double
  *                        (tabulated, source/p3mMethod.cpp:240-245, or analytic, :220-238)
  *   P3M_SUM_NEWTON       a_i = -G_c sum_j m_j r_ij / (r_ij^2 + eps^2)^(3/2), G_c = 1/(4 pi): softened Newtonian
  *                        gravity in code units (source/ppMethod.cpp:100-113 with G -> G_c)
+ *   P3M_SUM_CUTOFF_SHELL acc[3i] = number of sources whose r_ij^2 lies within a relative `softening_code` (default
+ *                        2e-6) of cutoff^2.  The short-range law is discontinuous at the cutoff (it is simply
+ *                        truncated, source/p3mMethod.cpp:258), so whether such a source counts is decided by the
+ *                        rounding of r^2 -- in the reference's fp32 arithmetic as much as here; parity figures
+ *                        are quoted over the targets without one (bench.py)
  * Pairs at zero distance are skipped (a target that is one of the particles does not attract itself).
  * Multi-GPU: every rank returns the contribution of its own particles; the caller adds the ranks up. */
-enum { P3M_SUM_SHORT_RANGE = 0, P3M_SUM_NEWTON = 1 };
+enum { P3M_SUM_SHORT_RANGE = 0, P3M_SUM_NEWTON = 1, P3M_SUM_CUTOFF_SHELL = 2 };
 int p3m_direct_sum(p3m_ctx* ctx, int mode, const double* target_pos_code, int64_t m, double softening_code,
                    double* acc_code);
 

@@ -45,7 +45,7 @@ class P3MParams(C.Structure):
 
 
 IC_PLUMMER, IC_DISK_LINEAR, IC_UNIFORM, IC_DISK_HALO = 0, 1, 2, 3
-SUM_SHORT_RANGE, SUM_NEWTON = 0, 1
+SUM_SHORT_RANGE, SUM_NEWTON, SUM_CUTOFF_SHELL = 0, 1, 2
 
 
 class P3MIc(C.Structure):

@@ -690,8 +690,9 @@ int p3m_direct_sum(p3m_ctx* c, int mode, const double* tpos, int64_t m, double e
   CHECK_CTX(c);
   if (!c->have_particles) return fail(P3M_ESTATE, "no particles set");
   if (m < 0 || (m > 0 && (!tpos || !out))) return fail(P3M_EINVAL, "p3m_direct_sum: bad argument");
-  if (mode != P3M_SUM_SHORT_RANGE && mode != P3M_SUM_NEWTON) return fail(P3M_EINVAL, "p3m_direct_sum: unknown mode %d", mode);
-  if (mode == P3M_SUM_SHORT_RANGE && !c->prm.p3m) return fail(P3M_ESTATE, "p3m_direct_sum: PM-only context has no short-range law");
+  if (mode != P3M_SUM_SHORT_RANGE && mode != P3M_SUM_NEWTON && mode != P3M_SUM_CUTOFF_SHELL)
+    return fail(P3M_EINVAL, "p3m_direct_sum: unknown mode %d", mode);
+  if (mode != P3M_SUM_NEWTON && !c->prm.p3m) return fail(P3M_ESTATE, "p3m_direct_sum: PM-only context has no short-range law");
   return P3M_DISPATCH(c, direct_sum, mode, tpos, (long long)m, eps, out);
 }
 

@@ -49,6 +49,12 @@ k_direct_sum(const V4<T>* __restrict__ posm, long long n, const double* __restri
     const double r2 = dx * dx + dy * dy + dz * dz;
     if (!(r2 > 0.0)) continue;
     double f;
+    if (s.mode == P3M_SUM_CUTOFF_SHELL) {
+      // the short-range law is discontinuous at the cutoff: a source this close to it is in or out depending on
+      // the rounding of r^2 (in the reference's own fp32 arithmetic as well); count them
+      if (fabs(r2 / s.re2 - 1.0) <= s.eps2) ax += 1.0;
+      continue;
+    }
     if (s.mode == P3M_SUM_NEWTON) {
       const double q = r2 + s.eps2;
       f = -G * (double)p.w / (q * sqrt(q));
@@ -86,6 +92,7 @@ int direct_sum(p3m_ctx* c, int mode, const double* tpos, long long m, double eps
   const SRParams<T>& sp = Sel<T>::sr(c);
   SumCfg cfg{mode, sp.use_table, sp.cloud, (double)sp.re2, (double)sp.inv_delta2, (double)sp.a,
              mode == P3M_SUM_NEWTON ? eps * eps : (double)sp.eps2};
+  if (mode == P3M_SUM_CUTOFF_SHELL) cfg.eps2 = eps > 0 ? eps : 2e-6;  // relative half-width of the shell in r^2
   double *d_t = nullptr, *d_out = nullptr, *d_tab = nullptr;
   P3M_CUDA(cudaMallocAsync((void**)&d_t, sizeof(double) * 3 * (size_t)m, c->stream));
   P3M_CUDA(cudaMallocAsync((void**)&d_out, sizeof(double) * 3 * (size_t)m, c->stream));
