@@ -334,19 +334,39 @@ int bin_sort(p3m_ctx* c) {
     const unsigned blocks = (unsigned)((n + 255) / 256);
     size_t tmp = s.cub_tmp_bytes;
     bool merged = false;
+    // highest mesh plane a particle sits in (single GPU: bounds the planes that are cleared / transformed)
+    const bool want_zmax = c->nranks == 1 && c->fused_z && !c->tune.no_prune;
+    s.inc_counts_host[3] = 0;
+    if (want_zmax) {
+      const int init = -1;
+      P3M_CUDA(cudaMemcpyAsync(s.inc_counts + 2, &init, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
     if (s.inc_backoff > 0) --s.inc_backoff;
     else if (short_key && c->order_valid && !c->tune.full_sort && s.skeys_n == n && s.skeys_bits == keybits)
       P3M_TRY(sort_incremental<T>(c, keybits, &merged));  // movers only (incsort.cu)
     if (!merged) {
+      // the occupied-plane bound is complete once k_keys has run: it is fetched right behind that kernel and waited
+      // for (this copy only) at the end of the call, while the radix sort and the permutation are already queued
+      auto fetch_zmax = [&]() -> int {
+        if (!want_zmax || s.inc_counts_host[3]) return 0;
+        if (!s.zmax_event) P3M_CUDA(cudaEventCreateWithFlags(&s.zmax_event, cudaEventDisableTiming));
+        P3M_CUDA(cudaMemcpyAsync(s.inc_counts_host, s.inc_counts, sizeof(int) * 3, cudaMemcpyDeviceToHost, c->stream));
+        P3M_CUDA(cudaEventRecord(s.zmax_event, c->stream));
+        return 0;
+      };
       if (short_key) {
-        k_keys<T, uint32_t><<<blocks, 256, 0, c->stream>>>(s.posm, s.id, n, g, keys32, s.slots, s.flags);
+        k_keys<T, uint32_t><<<blocks, 256, 0, c->stream>>>(s.posm, s.id, n, g, keys32, s.slots, s.flags,
+                                                           want_zmax ? s.inc_counts + 2 : nullptr);
         P3M_LAUNCH_CHECK(c);
+        P3M_TRY(fetch_zmax());
         // sorted keys go straight into the persistent array the next (incremental) sort compares against
         P3M_CUDA(cub::DeviceRadixSort::SortPairs(s.cub_tmp, tmp, keys32, s.skeys, s.slots, s.slots_alt, (int)n, 0,
                                                  keybits, c->stream));
       } else {
-        k_keys<T, uint64_t><<<blocks, 256, 0, c->stream>>>(s.posm, s.id, n, g, s.keys, s.slots, s.flags);
+        k_keys<T, uint64_t><<<blocks, 256, 0, c->stream>>>(s.posm, s.id, n, g, s.keys, s.slots, s.flags,
+                                                           want_zmax ? s.inc_counts + 2 : nullptr);
         P3M_LAUNCH_CHECK(c);
+        P3M_TRY(fetch_zmax());
         P3M_CUDA(cub::DeviceRadixSort::SortPairs(s.cub_tmp, tmp, s.keys, s.keys_alt, s.slots, s.slots_alt,
                                                  (int)n, 0, keybits, c->stream));
       }
@@ -374,6 +394,15 @@ int bin_sort(p3m_ctx* c) {
     k_cell_start<uint64_t><<<(unsigned)((ncells + 1 + 255) / 256), 256, 0, c->stream>>>(s.keys_alt, n, lowbits, ncells,
                                                                                        s.cell_start);
   P3M_LAUNCH_CHECK(c);
+  s.zocc = 0;
+  if (n > 0 && c->nranks == 1 && c->fused_z && !c->tune.no_prune) {
+    if (!s.inc_counts_host[3] && s.zmax_event) P3M_CUDA(cudaEventSynchronize(s.zmax_event));  // full-sort path: see above
+    const int zmax = s.inc_counts_host[2];
+    // TSC / CIC write planes (int)z - 1 .. (int)z + 1 (one more when the unwrapped flat index of a particle at the
+    // top of y aliases into the next plane): planes [0, zmax + 3) may hold density; rounded up to 16 so
+    // that the cached batched FFT plans change rarely
+    if (zmax >= 0 && zmax + 3 < c->prm.nz) s.zocc = std::min(c->prm.nz, (zmax + 3 + 15) / 16 * 16);
+  }
   phase_end(c, PH_BINSORT);
   c->sorted = true;
   c->order_valid = short_key && n > 0;
@@ -476,6 +505,8 @@ void free_state(p3m_ctx* c) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (s.inc_counts_host) cudaFreeHost(s.inc_counts_host);
+  for (auto& bp : s.batch_plans) cufftDestroy(bp.h);
+  if (s.zmax_event) cudaEventDestroy(s.zmax_event);
   if (s.twiddle_z) cudaFree(s.twiddle_z);
   if (s.plans) {
     cufftDestroy(s.plan_fwd);

@@ -38,6 +38,7 @@ void p3m_tune_load_impl(p3m_tune& t) {
   t.scalar_pp = flag("P3M_TUNE_SCALAR_PP");
   t.z_wide = flag("P3M_TUNE_Z_WIDE");
   t.contig_slabs = flag("P3M_TUNE_CONTIG_SLABS");
+  t.no_prune = flag("P3M_TUNE_NO_PRUNE");
   if (const char* e = getenv("P3M_TUNE_INC_SORT_DEN")) t.inc_sort_den = atoi(e) > 1 ? atoi(e) : 2;
   if (const char* e = getenv("P3M_TUNE_A2A_CHUNKS")) t.a2a_chunks = atoi(e);
   if (const char* e = getenv("P3M_TUNE_DENSE_CELL")) t.dense_cell = atoi(e) > 0 ? atoi(e) : 1;
@@ -546,6 +547,7 @@ int p3m_get_density(p3m_ctx* c, float* m) {
 }
 int p3m_get_potential(p3m_ctx* c, float* m) {
   CHECK_CTX(c);
+  P3M_TRY(P3M_DISPATCH(c, complete_potential));  // planes the pruned solve skipped
   return c->f64 ? get_mesh<double, float>(c, c->s64.potential, m, c->g64.M)
                 : get_mesh<float, float>(c, c->s32.potential, m, c->g32.M);
 }
@@ -562,6 +564,7 @@ int p3m_get_density_f64(p3m_ctx* c, double* m) {
 }
 int p3m_get_potential_f64(p3m_ctx* c, double* m) {
   CHECK_CTX(c);
+  P3M_TRY(P3M_DISPATCH(c, complete_potential));
   return c->f64 ? get_mesh<double, double>(c, c->s64.potential, m, c->g64.M)
                 : get_mesh<float, double>(c, c->s32.potential, m, c->g32.M);
 }
@@ -570,6 +573,8 @@ int p3m_set_density(p3m_ctx* c, const float* m) {
   int r = c->f64 ? set_mesh<double, float>(c, c->s64.density, m, c->g64.M)
                  : set_mesh<float, float>(c, c->s32.density, m, c->g32.M);
   if (r == 0) c->have_density = true;
+  // a density that did not come from the particles: nothing is known about its empty planes
+  c->s32.dens_occ = c->s64.dens_occ = 0, c->s32.dens_dirty = c->s64.dens_dirty = -1;
   return r;
 }
 int p3m_set_potential(p3m_ctx* c, const float* m) {
@@ -578,6 +583,7 @@ int p3m_set_potential(p3m_ctx* c, const float* m) {
                  : set_mesh<float, float>(c, c->s32.potential, m, c->g32.M);
   if (r == 0 && c->slab) r = c->f64 ? slab_spread_potential<double>(c) : slab_spread_potential<float>(c);
   if (r == 0) c->have_potential = true;
+  c->s32.pot_partial = c->s64.pot_partial = false;
   return r;
 }
 

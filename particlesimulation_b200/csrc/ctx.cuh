@@ -41,6 +41,7 @@ struct State {
   int* inc_hist = nullptr;
   int* inc_counts = nullptr;
   int* inc_counts_host = nullptr;
+  cudaEvent_t zmax_event = nullptr;  // the D2H copy of the occupied-plane bound has landed (full-sort path)
   int* cell_start = nullptr;  // (1 << 3*mbits) + 1 entries
   V4<T>* aabb = nullptr;      // 2 per kPPTile-particle tile: (lo.xyz, -), (hi.xyz, -)
   // ghost particles of the two neighbouring z-slabs (dist.cu), sorted by the same key
@@ -76,6 +77,18 @@ struct State {
   double* diag = nullptr;  // 16 doubles
   cufftHandle plan_fwd = 0, plan_inv = 0;
   bool plans = false;
+  // Pruned z range (single GPU): the padding half of the mesh (isolated boundary conditions) holds no density, so
+  // only the planes [0, zocc) are cleared, deposited into and 2-D transformed forward, and only the planes the gather
+  // reads -- [0, pot_lo) and the periodic tail [nz - pot_tail, nz) -- are transformed back; the others are completed
+  // on demand (potential readback, explicit gradient).  zocc comes from the particles (max plane seen by the sort,
+  // rounded up to 16), 0 = unknown = no pruning.  Batched plans are cached per plane count.
+  int zocc = 0;
+  int dens_occ = 0;           // the same bound for what `density` currently holds (0: unknown, e.g. p3m_set_density)
+  int dens_dirty = -1;        // leading planes of `density` that may be non-zero (-1: all)
+  bool pot_partial = false;
+  int pot_lo = 0, pot_tail = 0;
+  struct BatchPlan { int kind, batch; cufftHandle h; };
+  std::vector<BatchPlan> batch_plans;
   // fused z pass (poisson_z.cu): plan_fwd / plan_inv are then batched 2-D transforms over `fft_chunk` planes
   void* twiddle_z = nullptr;  // W_nz^k, k < nz
   int fft_chunk = 0;
@@ -96,6 +109,7 @@ struct p3m_tune {
   double particle_weight = 300.0;  // P3M_TUNE_PARTICLE_WEIGHT: mesh-side work of a particle, in pair evaluations
   long long fft_chunk_bytes = 1ll << 60;  // P3M_TUNE_FFT_CHUNK_MB: split the 2-D plane batches
   bool replicated_mesh = false; // P3M_REPLICATED_MESH: full mesh + all-reduce instead of slabs
+  bool no_prune = false;        // P3M_TUNE_NO_PRUNE: clear / transform every plane of the mesh (single GPU)
   bool contig_slabs = false;    // P3M_TUNE_CONTIG_SLABS: one contiguous run of planes per rank (round-1 FFT slab layout)
   bool cufft_z = false;         // P3M_TUNE_CUFFT_Z: z leg through cuFFT + multiply kernel
   bool full_sort = false;       // P3M_TUNE_FULL_SORT: radix-sort from scratch every step
@@ -236,7 +250,8 @@ template <typename T> int dist_allreduce_density(p3m_ctx* c);
 // poisson_z.cu: forward z FFT + influence-function multiply + inverse z FFT in one pass
 bool fused_z_supported(int nz);
 template <typename T> int fused_z_init(p3m_ctx* c);
-template <typename T> int fused_z_pass(p3m_ctx* c, void* spec, const T* green, long long ncols);
+template <typename T> int fused_z_pass(p3m_ctx* c, void* spec, const T* green, long long ncols, int nz_in = 0);
+template <typename T> int complete_potential(p3m_ctx* c);  // poisson.cu: materialise the planes the pruned solve skipped
 int fft_chunk_planes(long long plane_bytes, int planes, long long budget);
 // dist_mesh.cu: slab-decomposed mesh
 template <typename T> int slab_setup(p3m_ctx* c);             // after dist_init: plane ranges, buffers, plans

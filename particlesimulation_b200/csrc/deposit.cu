@@ -21,6 +21,8 @@
 #include <cstdlib>
 
 #include "async_copy.cuh"
+#include <algorithm>
+
 #include "ctx.cuh"
 #include "stencil.cuh"
 
@@ -441,7 +443,17 @@ int deposit(p3m_ctx* c) {
   const Geom<T>& g = Sel<T>::g(c);
   phase_begin(c, PH_DEPOSIT);
   // Grid::clearDensity (source/grid.cpp:34-36)
-  P3M_CUDA(cudaMemsetAsync(s.dens_part, 0, sizeof(T) * (size_t)g.den_len, c->stream));
+  // single GPU with a known occupied z range (State::zocc, from the sort): only the planes that were or will be
+  // written are cleared -- the padding half of the mesh stays zero from the first clear
+  {
+    size_t clear = (size_t)g.den_len;
+    const size_t plane = (size_t)g.nx * g.ny;
+    if (c->nranks == 1 && s.zocc > 0 && s.dens_dirty >= 0) clear = plane * (size_t)std::max(s.zocc, s.dens_dirty);
+    if (clear > (size_t)g.den_len) clear = (size_t)g.den_len;
+    P3M_CUDA(cudaMemsetAsync(s.dens_part, 0, sizeof(T) * clear, c->stream));
+    s.dens_dirty = c->nranks == 1 && s.zocc > 0 ? s.zocc : -1;
+    s.dens_occ = c->nranks == 1 ? s.zocc : 0;
+  }
   c->launches++;
   int r = 0;
   const bool pm_cells = !g.p3m && g.tile_shift == kPmTileShift && g.sbits == g.tile_shift && g.is != P3M_NGP &&

@@ -668,6 +668,7 @@ template <typename T>
 int gradient(p3m_ctx* c) {
   if (!c->have_potential) return fail(P3M_ESTATE, "p3m_gradient: no potential (call p3m_poisson)");
   if (c->slab) return fail(P3M_ESTATE, "p3m_gradient: the explicit field mesh is not built on a slab-decomposed mesh");
+  P3M_TRY(complete_potential<T>(c));  // the explicit field mesh needs every plane of the potential
   State<T>& s = Sel<T>::st(c);
   const Geom<T>& g = Sel<T>::g(c);
   if (!s.field) P3M_CUDA(cudaMalloc((void**)&s.field, sizeof(T) * 3 * (size_t)g.M));

@@ -34,17 +34,19 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_inc_keys(const V4<T>* __restrict__ posm, long long n, Geom<T> g, const uint32_t* __restrict__ skeys,
            uint32_t* __restrict__ keys, uint32_t* __restrict__ mask, int* __restrict__ blockcnt,
-           int* __restrict__ flags) {
+           int* __restrict__ flags, int* __restrict__ zmax) {
   const long long base = blockIdx.x * (long long)kIncBlock;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int movers = 0;
+  int movers = 0, zloc = -1;
 #pragma unroll
   for (int r = 0; r < kIncBlock / 256; ++r) {
     const long long i = base + r * 256 + threadIdx.x;
     bool mv = false;
     if (i < n) {
       bool inside;
-      const uint32_t k = (uint32_t)cell_key(g, posm[i], inside);
+      const V4<T> pp = posm[i];
+      const uint32_t k = (uint32_t)cell_key(g, pp, inside);
+      zloc = max(zloc, plane_of(pp));
       if (!inside) flags[1] = 1;
       keys[i] = k;
       mv = k != skeys[i];
@@ -61,6 +63,7 @@ k_inc_keys(const V4<T>* __restrict__ posm, long long n, Geom<T> g, const uint32_
     for (int w = 0; w < 8; ++w) t += red[w];
     blockcnt[blockIdx.x] = t;
   }
+  if (zmax) block_zmax(zloc, zmax);
 }
 
 // in-place exclusive scan of `count` ints by ONE CTA of 1024 threads, 8 consecutive entries per thread and
@@ -419,13 +422,14 @@ int sort_incremental(p3m_ctx* c, int keybits, bool* done) {
   int* moff = reinterpret_cast<int*>(upper + W);
   int* blockcnt = reinterpret_cast<int*>(upper + 2 * W);
   const int nb = (int)((n + kIncBlock - 1) / kIncBlock);
-  k_inc_keys<T><<<nb, 256, 0, c->stream>>>(s.posm, n, g, s.skeys, keys32, mask, blockcnt, s.flags);
+  k_inc_keys<T><<<nb, 256, 0, c->stream>>>(s.posm, n, g, s.skeys, keys32, mask, blockcnt, s.flags, s.inc_counts + 2);
   P3M_LAUNCH_CHECK(c);
   k_excl_scan<<<1, 1024, 0, c->stream>>>(blockcnt, nb, s.inc_counts);
   P3M_LAUNCH_CHECK(c);
-  P3M_CUDA(cudaMemcpyAsync(s.inc_counts_host, s.inc_counts, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  P3M_CUDA(cudaMemcpyAsync(s.inc_counts_host, s.inc_counts, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream));
   P3M_CUDA(cudaStreamSynchronize(c->stream));
   const int m = s.inc_counts_host[0];
+  s.inc_counts_host[3] = 1;  // [2] = highest occupied plane is fresh (bin_sort)
   c->stat_movers = (double)m;
   // many movers (e.g. the 16^3 sub-cell key of a warm P3M set): the full sort is cheaper -- measured break-even on
   // B200 at 2^24 particles: ~1/10 of the particles (merge 0.97 ms vs radix sort 0.89 ms at 11.5 % movers); do not

@@ -317,6 +317,45 @@ int alloc_meshes(p3m_ctx* c) {
   return 0;
 }
 
+// batched 2-D plan over `batch` planes (kind 0: R2C, 1: C2R), cached per (kind, batch)
+template <typename T>
+static int batch_plan(p3m_ctx* c, int kind, int batch, cufftHandle* out) {
+  State<T>& s = Sel<T>::st(c);
+  for (const auto& bp : s.batch_plans)
+    if (bp.kind == kind && bp.batch == batch) {
+      *out = bp.h;
+      return 0;
+    }
+  const bool dbl = sizeof(T) == 8;
+  int n2[2] = {c->prm.ny, c->prm.nx};
+  cufftHandle h;
+  P3M_FFT(cufftPlanMany(&h, 2, n2, nullptr, 1, 0, nullptr, 1, 0,
+                        kind == 0 ? (dbl ? CUFFT_D2Z : CUFFT_R2C) : (dbl ? CUFFT_Z2D : CUFFT_C2R), batch));
+  P3M_FFT(cufftSetStream(h, c->stream));
+  s.batch_plans.push_back({kind, batch, h});
+  *out = h;
+  return 0;
+}
+
+// the pruned solve transformed back only the planes the gather reads; a caller that wants the whole potential mesh
+// (readback, explicit gradient) gets the remaining planes now -- the spectrum still holds them
+template <typename T>
+int complete_potential(p3m_ctx* c) {
+  State<T>& s = Sel<T>::st(c);
+  if (!s.pot_partial) return 0;
+  const p3m_params& p = c->prm;
+  const size_t plane = (size_t)p.nx * p.ny, splane = (size_t)(p.nx / 2 + 1) * p.ny;
+  const int mid = p.nz - s.pot_tail - s.pot_lo;
+  if (mid > 0) {
+    cufftHandle pm;
+    P3M_TRY(batch_plan<T>(c, 1, mid, &pm));
+    P3M_FFT(exec_inv(pm, s.spectrum + splane * (size_t)s.pot_lo, s.potential + plane * (size_t)s.pot_lo));
+    c->launches += 2;
+  }
+  s.pot_partial = false;
+  return 0;
+}
+
 template <typename T>
 int poisson(p3m_ctx* c) {
   if (!c->have_green) return fail(P3M_ESTATE, "p3m_poisson: call p3m_green_init first");
@@ -332,6 +371,33 @@ int poisson(p3m_ctx* c) {
   if (c->fused_z) {
     const p3m_params& p = c->prm;
     const size_t plane = (size_t)p.nx * p.ny, splane = (size_t)(p.nx / 2 + 1) * p.ny;
+    // pruned z range (State::zocc): planes >= zocc hold no density -- their 2-D transform is zero and is neither
+    // computed nor read by the z pass; of the result only the planes the gather touches are transformed back
+    const int FD = c->prm.fd_scheme == P3M_TWO_POINT ? 1 : 2;
+    const int lo = s.dens_occ + FD + 2, tail = FD + 2;
+    const bool prune = s.dens_occ > 0 && lo + tail + 16 <= p.nz && !c->tune.no_prune;
+    s.pot_partial = false;
+    if (prune) {
+      cufftHandle pf, pl, pt;
+      P3M_TRY(batch_plan<T>(c, 0, s.dens_occ, &pf));
+      P3M_TRY(batch_plan<T>(c, 1, lo, &pl));
+      P3M_TRY(batch_plan<T>(c, 1, tail, &pt));
+      phase_begin(c, PH_FFT_FWD);
+      P3M_FFT(exec_fwd(pf, s.density, s.spectrum));
+      c->launches += 2;
+      phase_end(c, PH_FFT_FWD);
+      phase_begin(c, PH_MULTIPLY);  // forward z FFT + multiply + inverse z FFT; input planes >= zocc taken as zero
+      P3M_TRY(fused_z_pass<T>(c, s.spectrum, s.green, (long long)splane, s.dens_occ));
+      phase_end(c, PH_MULTIPLY);
+      phase_begin(c, PH_FFT_INV);
+      P3M_FFT(exec_inv(pl, s.spectrum, s.potential));
+      P3M_FFT(exec_inv(pt, s.spectrum + splane * (size_t)(p.nz - tail), s.potential + plane * (size_t)(p.nz - tail)));
+      c->launches += 4;
+      phase_end(c, PH_FFT_INV);
+      s.pot_partial = true, s.pot_lo = lo, s.pot_tail = tail;
+      c->have_potential = true;
+      return 0;
+    }
     phase_begin(c, PH_FFT_FWD);
     for (int z = 0; z < p.nz; z += s.fft_chunk) {
       P3M_FFT(exec_fwd(s.plan_fwd, s.density + plane * z, s.spectrum + splane * z));
@@ -462,6 +528,7 @@ int fft3d_c2c(int nz, int ny, int nx, const float* in, float* out, int inverse) 
   template int green_get<T>(p3m_ctx*, double*);                         \
   template int alloc_meshes<T>(p3m_ctx*);                               \
   template int poisson<T>(p3m_ctx*);                                    \
+  template int complete_potential<T>(p3m_ctx*);                              \
   template int get_mesh<T, float>(p3m_ctx*, const T*, float*, long long);   \
   template int get_mesh<T, double>(p3m_ctx*, const T*, double*, long long); \
   template int set_mesh<T, float>(p3m_ctx*, T*, const float*, long long);   \

@@ -181,7 +181,8 @@ __device__ __forceinline__ void run_stages(Cx<T> (&e)[8], const Cx<T>* tw, T* re
 
 template <typename T, int LOGN, int C>
 __global__ void __launch_bounds__(C * (1 << LOGN) / 8)
-k_poisson_z(Cx<T>* __restrict__ spec, const T* __restrict__ green, const Cx<T>* __restrict__ twg, long long ncols) {
+k_poisson_z(Cx<T>* __restrict__ spec, const T* __restrict__ green, const Cx<T>* __restrict__ twg, long long ncols,
+            int nz_in) {
   constexpr int N = 1 << LOGN;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Cx<T>* tw = reinterpret_cast<Cx<T>*>(smem_raw);
@@ -201,7 +202,8 @@ k_poisson_z(Cx<T>* __restrict__ spec, const T* __restrict__ green, const Cx<T>* 
   for (int u = 0; u < 8 / R0; ++u)
 #pragma unroll
     for (int r = 0; r < R0; ++r)
-      e[u * R0 + r] = valid ? base[ncols * slot_index<N, R0>(t, u, r)] : Cx<T>{0, 0};
+      // planes >= nz_in are known to be zero (zero padding of the isolated boundary conditions): not even read
+      e[u * R0 + r] = valid && slot_index<N, R0>(t, u, r) < nz_in ? base[ncols * slot_index<N, R0>(t, u, r)] : Cx<T>{0, 0};
   run_stages<T, LOGN, C, false, 0>(e, tw, re, im, t, c);
 
   // ---- influence function (A3) on the registers, conjugated for the inverse ------------------------------
@@ -241,7 +243,7 @@ int log2_exact(int N) {
 }
 
 template <typename T, int LOGN, int C>
-int launch_z(p3m_ctx* c, void* spec, const T* green, long long ncols) {
+int launch_z(p3m_ctx* c, void* spec, const T* green, long long ncols, int nz_in) {
   State<T>& s = Sel<T>::st(c);
   constexpr int N = 1 << LOGN;
   const size_t smem = sizeof(Cx<T>) * (size_t)N + 2 * sizeof(T) * (size_t)(N + N / 8) * C;
@@ -249,7 +251,8 @@ int launch_z(p3m_ctx* c, void* spec, const T* green, long long ncols) {
   P3M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long blocks = (ncols + C - 1) / C;
   kern<<<(unsigned)blocks, C * N / 8, smem, c->stream>>>(reinterpret_cast<Cx<T>*>(spec), green,
-                                                        reinterpret_cast<const Cx<T>*>(s.twiddle_z), ncols);
+                                                        reinterpret_cast<const Cx<T>*>(s.twiddle_z), ncols,
+                                                        nz_in > 0 && nz_in < N ? nz_in : N);
   P3M_LAUNCH_CHECK(c);
   return 0;
 }
@@ -277,27 +280,27 @@ int fused_z_init(p3m_ctx* c) {
 // forward z FFT, multiply by `green`, inverse z FFT, in place on `spec` ([col + ncols * kz]).
 // N/8 threads per column, C columns per CTA (one contiguous C*8-byte run for every kz), 512 threads.
 template <typename T>
-int fused_z_pass(p3m_ctx* c, void* spec, const T* green, long long ncols) {
+int fused_z_pass(p3m_ctx* c, void* spec, const T* green, long long ncols, int nz_in) {
   constexpr bool D = sizeof(T) == 8;
   switch (log2_exact(c->prm.nz)) {
-    case 4: return launch_z<T, 4, 32>(c, spec, green, ncols);
-    case 5: return launch_z<T, 5, 32>(c, spec, green, ncols);
-    case 6: return launch_z<T, 6, 32>(c, spec, green, ncols);
-    case 7: return launch_z<T, 7, 32>(c, spec, green, ncols);
-    case 8: return launch_z<T, 8, D ? 8 : 16>(c, spec, green, ncols);
+    case 4: return launch_z<T, 4, 32>(c, spec, green, ncols, nz_in);
+    case 5: return launch_z<T, 5, 32>(c, spec, green, ncols, nz_in);
+    case 6: return launch_z<T, 6, 32>(c, spec, green, ncols, nz_in);
+    case 7: return launch_z<T, 7, 32>(c, spec, green, ncols, nz_in);
+    case 8: return launch_z<T, 8, D ? 8 : 16>(c, spec, green, ncols, nz_in);
     case 9:
-      if (c->tune.z_wide && !D) return launch_z<T, 9, 16>(c, spec, green, ncols);  // 128-byte runs, 1024 threads
-      return launch_z<T, 9, D ? 4 : 8>(c, spec, green, ncols);
+      if (c->tune.z_wide && !D) return launch_z<T, 9, 16>(c, spec, green, ncols, nz_in);  // 128-byte runs, 1024 threads
+      return launch_z<T, 9, D ? 4 : 8>(c, spec, green, ncols, nz_in);
     case 10:
-      if (c->tune.z_wide && !D) return launch_z<T, 10, 8>(c, spec, green, ncols);
-      return launch_z<T, 10, 4>(c, spec, green, ncols);
+      if (c->tune.z_wide && !D) return launch_z<T, 10, 8>(c, spec, green, ncols, nz_in);
+      return launch_z<T, 10, 4>(c, spec, green, ncols, nz_in);
     default: return fail(P3M_EINVAL, "fused z pass: nz = %d is not a power of two in [16, 1024]", c->prm.nz);
   }
 }
 
 template int fused_z_init<float>(p3m_ctx*);
 template int fused_z_init<double>(p3m_ctx*);
-template int fused_z_pass<float>(p3m_ctx*, void*, const float*, long long);
-template int fused_z_pass<double>(p3m_ctx*, void*, const double*, long long);
+template int fused_z_pass<float>(p3m_ctx*, void*, const float*, long long, int);
+template int fused_z_pass<double>(p3m_ctx*, void*, const double*, long long, int);
 
 }  // namespace p3m

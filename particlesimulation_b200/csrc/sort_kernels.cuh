@@ -35,20 +35,42 @@ __device__ __forceinline__ uint64_t cell_key(const Geom<T>& g, const V4<T>& p, b
   return m;
 }
 
+// highest mesh plane (int)z of a particle, clamped to [0, 2^30)
+template <typename T>
+__device__ __forceinline__ int plane_of(const V4<T>& p) {
+  const float zf = (float)p.z;
+  return zf < 0.f ? 0 : (zf > 1e9f ? 0x3fffffff : (int)zf);
+}
+// block maximum -> *zmax with ONE guarded atomic per CTA (most CTAs only read); call from every thread of the CTA
+__device__ __forceinline__ void block_zmax(int z, int* __restrict__ zmax) {
+  __shared__ int s_zmax;
+  if (threadIdx.x == 0) s_zmax = -1;
+  __syncthreads();
+  const int wz = __reduce_max_sync(0xffffffffu, z);
+  if ((threadIdx.x & 31) == 0 && wz >= 0) atomicMax(&s_zmax, wz);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_zmax > *reinterpret_cast<volatile int*>(zmax)) atomicMax(zmax, s_zmax);
+}
+
 template <typename T, typename KeyT>
 __global__ void k_keys(const V4<T>* __restrict__ posm, const int* __restrict__ id, long long n,
                        Geom<T> g, KeyT* __restrict__ keys, uint32_t* __restrict__ slots,
-                       int* __restrict__ flags) {
+                       int* __restrict__ flags, int* __restrict__ zmax = nullptr) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  bool inside;
-  const uint64_t m = cell_key(g, posm[i], inside);
-  if (!inside) flags[1] = 1;
-  if (sizeof(KeyT) == 8)
-    keys[i] = (KeyT)((m << g.idbits) | (uint64_t)(uint32_t)id[i]);
-  else
-    keys[i] = (KeyT)m;
-  slots[i] = (uint32_t)i;
+  int z = -1;
+  if (i < n) {
+    bool inside;
+    const V4<T> pp = posm[i];
+    const uint64_t m = cell_key(g, pp, inside);
+    z = plane_of(pp);
+    if (!inside) flags[1] = 1;
+    if (sizeof(KeyT) == 8)
+      keys[i] = (KeyT)((m << g.idbits) | (uint64_t)(uint32_t)id[i]);
+    else
+      keys[i] = (KeyT)m;
+    slots[i] = (uint32_t)i;
+  }
+  if (zmax) block_zmax(z, zmax);  // uniform over the CTA
 }
 
 template <typename T>
