@@ -265,11 +265,11 @@ def load_peaks():
 
 
 def profile_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the newest committed
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the last (by tag) committed
     `ncu --set full` summary under profiles/ (tools/summarize_ncu.py); None if there is none."""
     import glob
     import re
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"{kernel}_*.txt")), key=os.path.getmtime)
+    files = sorted(f for f in glob.glob(os.path.join(ROOT, "profiles", f"{kernel}_*.txt")) if "_sass_" not in f)  # by tag
     if not files:
         return None, None
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
