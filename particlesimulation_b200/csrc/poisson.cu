@@ -375,13 +375,16 @@ int poisson(p3m_ctx* c) {
     // computed nor read by the z pass; of the result only the planes the gather touches are transformed back
     const int FD = c->prm.fd_scheme == P3M_TWO_POINT ? 1 : 2;
     const int lo = s.dens_occ + FD + 2, tail = FD + 2;
-    const bool prune = s.dens_occ > 0 && lo + tail + 16 <= p.nz && !c->tune.no_prune;
+    bool prune = s.dens_occ > 0 && lo + tail + 16 <= p.nz && !c->tune.no_prune;
     s.pot_partial = false;
+    cufftHandle pf = 0, pl = 0, pt = 0;
+    // a plan that cannot be made (work-area memory) is no reason to fail the solve: transform every plane instead
+    if (prune && (batch_plan<T>(c, 0, s.dens_occ, &pf) != 0 || batch_plan<T>(c, 1, lo, &pl) != 0 ||
+                  batch_plan<T>(c, 1, tail, &pt) != 0)) {
+      prune = false;
+      cudaGetLastError();
+    }
     if (prune) {
-      cufftHandle pf, pl, pt;
-      P3M_TRY(batch_plan<T>(c, 0, s.dens_occ, &pf));
-      P3M_TRY(batch_plan<T>(c, 1, lo, &pl));
-      P3M_TRY(batch_plan<T>(c, 1, tail, &pt));
       phase_begin(c, PH_FFT_FWD);
       P3M_FFT(exec_fwd(pf, s.density, s.spectrum));
       c->launches += 2;
